@@ -1,0 +1,1076 @@
+/*
+ * pik_oracle.c -- CPU ORACLE for the pick_ik hot path.  TEST INFRASTRUCTURE ONLY.
+ * See pik_oracle.h for scope, pinning status and the arithmetic contract.
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -mfma -fPIC -shared pik_oracle.c -o _build/liboracle.so -lm -lpthread
+ * (-ffp-contract=off: no fused operations other than the fma() calls spelled out below.)
+ *
+ * Every function cites the reference lines it restates (pick_ik @ 8c99999).
+ */
+#include "pik_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------------------------------
+ * Deterministic elementary functions.  The reference calls libm sin/cos (inside moveit_core's
+ * RevoluteJointModel::computeTransform) and atan2 (Eigen angularDistance).  libm and CUDA's libm
+ * differ by ulps, which would make flags and GD trajectories diverge, so both the oracle and the
+ * kernels use these: Cody-Waite reduction + fdlibm-style minimax kernels, written only with
+ * + - * / fma.  |error| vs the exact function is ~1 ulp for |x| < 1e5.
+ * ------------------------------------------------------------------------------------------ */
+static const double INV_PIO2 = 0x1.45f306dc9c883p-1;
+static const double PIO2_1 = 0x1.921fb54442d18p+0;
+static const double PIO2_2 = 0x1.1a62633145c07p-54;
+static const double PIO2_3 = -0x1.f1976b7ed8fbcp-110;
+static const double S1 = -0x1.5555555555549p-3, S2 = 0x1.111111110f8a6p-7, S3 = -0x1.a01a019c161d5p-13,
+                    S4 = 0x1.71de357b1fe7dp-19, S5 = -0x1.ae5e68a2b9cebp-26, S6 = 0x1.5d93a5acfd57cp-33;
+static const double C1 = 0x1.555555555554cp-5, C2 = -0x1.6c16c16c15177p-10, C3 = 0x1.a01a019cb1590p-16,
+                    C4 = -0x1.27e4f809c52adp-22, C5 = 0x1.1ee9ebdb4b1c4p-29, C6 = -0x1.8fae9be8838d4p-37;
+
+static double orc_nan(void) {
+    union { uint64_t u; double d; } v;
+    v.u = 0x7ff8000000000000ull;
+    return v.d;
+}
+
+void orc_sincos(double x, double* s, double* c) {
+    if (!(fabs(x) < 1.0e15)) { /* also catches NaN / inf */
+        *s = orc_nan();
+        *c = orc_nan();
+        return;
+    }
+    double k = rint(x * INV_PIO2);
+    double r = fma(-k, PIO2_1, x);
+    r = fma(-k, PIO2_2, r);
+    r = fma(-k, PIO2_3, r);
+    long long q = (long long)k;
+    double z = r * r;
+    double ps = fma(z, S6, S5);
+    ps = fma(z, ps, S4);
+    ps = fma(z, ps, S3);
+    ps = fma(z, ps, S2);
+    ps = fma(z, ps, S1);
+    double sr = fma(r * z, ps, r);
+    double pc = fma(z, C6, C5);
+    pc = fma(z, pc, C4);
+    pc = fma(z, pc, C3);
+    pc = fma(z, pc, C2);
+    pc = fma(z, pc, C1);
+    double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    switch ((int)(q & 3)) {
+        case 0: *s = sr; *c = cr; break;
+        case 1: *s = cr; *c = -sr; break;
+        case 2: *s = -sr; *c = -cr; break;
+        default: *s = -cr; *c = sr; break;
+    }
+}
+
+static const double AT0 = 0x1.555555555550dp-2, AT1 = -0x1.999999998ebc4p-3, AT2 = 0x1.24924920083ffp-3,
+                    AT3 = -0x1.c71c6fe231671p-4, AT4 = 0x1.745cdc54c206ep-4, AT5 = -0x1.3b0f2af749a6dp-4,
+                    AT6 = 0x1.10d66a0d03d51p-4, AT7 = -0x1.dde2d52defd9ap-5, AT8 = 0x1.97b4b24760debp-5,
+                    AT9 = -0x1.2b4442c6a6c2fp-5, AT10 = 0x1.0ad3ae322da11p-6;
+static const double TAN_PIO8 = 0x1.a827999fcef34p-2;
+static const double PIO4_HI = 0x1.921fb54442d18p-1, PIO4_LO = 0x1.1a62633145c07p-55;
+static const double PIO2_HI = 0x1.921fb54442d18p+0, PIO2_LO = 0x1.1a62633145c07p-54;
+static const double PI_HI = 0x1.921fb54442d18p+1, PI_LO = 0x1.1a62633145c07p-53;
+
+/* atan of a in [0, 1] */
+static double atan_unit(double a) {
+    double t = a, hi = 0.0, lo = 0.0;
+    if (a > TAN_PIO8) {
+        t = (a - 1.0) / (a + 1.0);
+        hi = PIO4_HI;
+        lo = PIO4_LO;
+    }
+    double z = t * t;
+    double w = z * z;
+    /* fdlibm split: even and odd coefficient chains */
+    double s1 = fma(w, AT10, AT8);
+    s1 = fma(w, s1, AT6);
+    s1 = fma(w, s1, AT4);
+    s1 = fma(w, s1, AT2);
+    s1 = fma(w, s1, AT0);
+    s1 = z * s1;
+    double s2 = fma(w, AT9, AT7);
+    s2 = fma(w, s2, AT5);
+    s2 = fma(w, s2, AT3);
+    s2 = fma(w, s2, AT1);
+    s2 = w * s2;
+    double r = fma(-t, s1 + s2, t); /* t - t*(s1+s2) */
+    return hi + (r + lo);
+}
+
+double orc_atan2(double y, double x) {
+    if (x != x || y != y) return orc_nan();
+    double ax = fabs(x), ay = fabs(y);
+    double mx = ax > ay ? ax : ay;
+    double mn = ax > ay ? ay : ax;
+    double r;
+    if (mx == 0.0) {
+        r = 0.0;
+    } else {
+        double a = mn / mx; /* inf/inf -> NaN, documented */
+        r = atan_unit(a);
+        if (ay > ax) r = PIO2_HI - (r - PIO2_LO);
+    }
+    if (x < 0.0) r = PI_HI - (r - PI_LO);
+    return (y < 0.0) ? -r : r;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * RNG.  The reference uses rsl::uniform_real / uniform_int over a thread-local std::mt19937 seeded
+ * from random_device (src/robot.cpp:25-28, src/ik_memetic.cpp:131-159): unseeded, PARITY-UNPINNED.
+ * We define Philox4x32-10 word streams: key = rng_seed, counter = (block, stream_lo, stream_hi,
+ * problem).  uniform_real = 53-bit (as generate_canonical<double,53> over two 32-bit draws),
+ * uniform_int = Lemire multiply-shift with rejection (as libstdc++ >= 11 for 32-bit URBGs).
+ * ------------------------------------------------------------------------------------------ */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int round = 0; round < 10; ++round) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+enum { STREAM_INIT = 1, STREAM_REPRODUCE = 2, STREAM_TARGET = 3 };
+
+typedef struct {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t buf[4];
+    int pos;
+} orc_rng;
+
+static void rng_init(orc_rng* r, uint64_t seed, uint32_t problem, uint32_t purpose, uint32_t epoch,
+                     uint32_t individual) {
+    r->key[0] = (uint32_t)seed;
+    r->key[1] = (uint32_t)(seed >> 32);
+    r->ctr[0] = 0;
+    r->ctr[1] = individual;
+    r->ctr[2] = (purpose << 28) | (epoch & 0x0fffffffu);
+    r->ctr[3] = problem;
+    r->pos = 4;
+}
+
+static uint32_t rng_u32(orc_rng* r) {
+    if (r->pos == 4) {
+        orc_philox4x32_10(r->ctr, r->key, r->buf);
+        r->ctr[0] += 1;
+        r->pos = 0;
+    }
+    return r->buf[r->pos++];
+}
+
+/* u in [0,1), 53 bits: first word = low half */
+static double rng_unit(orc_rng* r) {
+    uint64_t lo = rng_u32(r);
+    uint64_t hi = rng_u32(r);
+    return (double)(((hi << 32) | lo) >> 11) * 0x1.0p-53;
+}
+
+/* rsl::uniform_real(a, b): a + (b - a) * u */
+static double rng_uniform_real(orc_rng* r, double a, double b) { return a + (b - a) * rng_unit(r); }
+
+/* rsl::uniform_int<size_t>(0, m - 1) */
+static uint32_t rng_uniform_int(orc_rng* r, uint32_t m) {
+    uint64_t prod = (uint64_t)rng_u32(r) * m;
+    uint32_t low = (uint32_t)prod;
+    if (low < m) {
+        uint32_t thr = (0u - m) % m;
+        while (low < thr) {
+            prod = (uint64_t)rng_u32(r) * m;
+            low = (uint32_t)prod;
+        }
+    }
+    return (uint32_t)(prod >> 32);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Frames (Eigen arithmetic restated)
+ * ------------------------------------------------------------------------------------------ */
+void orc_quat_to_matrix(const double q[4], double R[9]) {
+    /* Eigen QuaternionBase::toRotationMatrix; q = (w,x,y,z); no normalisation (tf2::fromMsg) */
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    double twx = tx * w, twy = ty * w, twz = tz * w;
+    double txx = tx * x, txy = ty * x, txz = tz * x;
+    double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1.0 - (tyy + tzz);
+    R[1] = txy - twz;
+    R[2] = txz + twy;
+    R[3] = txy + twz;
+    R[4] = 1.0 - (txx + tzz);
+    R[5] = tyz - twx;
+    R[6] = txz - twy;
+    R[7] = tyz + twx;
+    R[8] = 1.0 - (txx + tyy);
+}
+
+void orc_matrix_to_quat(const double R[9], double q[4]) {
+    /* Eigen quaternionbase_assign_impl<Matrix3d> */
+    double t = (R[0] + R[4]) + R[8];
+    if (t > 0.0) {
+        t = sqrt(t + 1.0);
+        q[0] = 0.5 * t;
+        t = 0.5 / t;
+        q[1] = (R[7] - R[5]) * t;
+        q[2] = (R[2] - R[6]) * t;
+        q[3] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        int j = (i + 1) % 3;
+        int k = (j + 1) % 3;
+        t = sqrt(((R[4 * i] - R[4 * j]) - R[4 * k]) + 1.0);
+        q[1 + i] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (R[3 * k + j] - R[3 * j + k]) * t;
+        q[1 + j] = (R[3 * j + i] + R[3 * i + j]) * t;
+        q[1 + k] = (R[3 * k + i] + R[3 * i + k]) * t;
+    }
+}
+
+/* goal.cpp:17-19 */
+double orc_linear_distance(const double t1[3], const double t2[3]) {
+    double dx = t1[0] - t2[0], dy = t1[1] - t2[1], dz = t1[2] - t2[2];
+    return sqrt((dx * dx + dy * dy) + dz * dz);
+}
+
+/* goal.cpp:21-25: q_2.angularDistance(q_1), q_1 = goal, q_2 = tip.
+ * Eigen >= 3.3: d = q_2 * conj(q_1); 2 * atan2(|d.vec|, |d.w|).  Products written out in
+ * Eigen's quaternion-product order with conj(q_1) = (w, -x, -y, -z) substituted. */
+double orc_angular_distance_q(const double g[4], const double R_tip[9]) {
+    double a[4];
+    orc_matrix_to_quat(R_tip, a);
+    double aw = a[0], ax = a[1], ay = a[2], az = a[3];
+    double bw = g[0], bx = -g[1], by = -g[2], bz = -g[3];
+    double dw = ((aw * bw - ax * bx) - ay * by) - az * bz;
+    double dx = ((aw * bx + ax * bw) + ay * bz) - az * by;
+    double dy = ((aw * by + ay * bw) + az * bx) - ax * bz;
+    double dz = ((aw * bz + az * bw) + ax * by) - ay * bx;
+    double vn = sqrt((dx * dx + dy * dy) + dz * dz);
+    return 2.0 * orc_atan2(vn, fabs(dw));
+}
+
+double orc_angular_distance(const double R_goal[9], const double R_tip[9]) {
+    double g[4];
+    orc_matrix_to_quat(R_goal, g);
+    return orc_angular_distance_q(g, R_tip);
+}
+
+/* goal.cpp:27-36.  threshold < 0 == std::nullopt */
+int orc_frame_test(const double goal_t[3], const double goal_R[9], const double tip_t[3],
+                   const double tip_R[9], double position_threshold, double orientation_threshold) {
+    if (position_threshold >= 0.0 && !(orc_linear_distance(goal_t, tip_t) <= position_threshold))
+        return 0;
+    if (orientation_threshold >= 0.0 &&
+        !(fabs(orc_angular_distance(goal_R, tip_R)) <= orientation_threshold))
+        return 0;
+    return 1;
+}
+
+static double pose_cost_q(const double goal_t[3], const double goal_q[4], const double tip_t[3],
+                          const double tip_R[9], double ps, double rs) {
+    /* goal.cpp:51-78; std::pow(x, 2) == x * x */
+    double cost = 0.0;
+    if (ps > 0.0) {
+        double d = orc_linear_distance(goal_t, tip_t) * ps;
+        if (rs > 0.0) {
+            double a = orc_angular_distance_q(goal_q, tip_R) * rs;
+            cost = d * d + a * a;
+        } else {
+            cost = d * d;
+        }
+    } else if (rs > 0.0) {
+        double a = orc_angular_distance_q(goal_q, tip_R) * rs;
+        cost = a * a;
+    }
+    return cost;
+}
+
+double orc_pose_cost(const double goal_t[3], const double goal_R[9], const double tip_t[3],
+                     const double tip_R[9], double position_scale, double rotation_scale) {
+    double g[4];
+    orc_matrix_to_quat(goal_R, g);
+    return pose_cost_q(goal_t, g, tip_t, tip_R, position_scale, rotation_scale);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Robot table (src/robot.cpp:44-85) and chain description
+ * ------------------------------------------------------------------------------------------ */
+static void mat_mul(const double A[9], const double B[9], double C[9]) {
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            C[3 * r + c] = fma(A[3 * r + 2], B[6 + c], fma(A[3 * r + 1], B[3 + c], A[3 * r] * B[c]));
+}
+static void mat_vec_add(const double A[9], const double v[3], const double t[3], double out[3]) {
+    for (int r = 0; r < 3; ++r)
+        out[r] = fma(A[3 * r + 2], v[2], fma(A[3 * r + 1], v[1], fma(A[3 * r], v[0], t[r])));
+}
+
+int orc_robot_build(const orc_joint_desc* joints, int n_joints, orc_robot* out) {
+    memset(out, 0, sizeof(*out));
+    double accR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, acct[3] = {0, 0, 0};
+    int have_acc = 0, n = 0;
+    for (int j = 0; j < n_joints; ++j) {
+        const orc_joint_desc* jd = &joints[j];
+        /* acc = acc * origin_j */
+        if (!have_acc) {
+            memcpy(accR, jd->origin_R, sizeof(accR));
+            memcpy(acct, jd->origin_t, sizeof(acct));
+            have_acc = 1;
+        } else {
+            double nR[9], nt[3];
+            mat_vec_add(accR, jd->origin_t, acct, nt);
+            mat_mul(accR, jd->origin_R, nR);
+            memcpy(accR, nR, sizeof(nR));
+            memcpy(acct, nt, sizeof(nt));
+        }
+        if (jd->type == ORC_JOINT_FIXED) continue;
+        if (n >= ORC_MAX_VARS) return -1;
+        orc_step* st = &out->steps[n];
+        memcpy(st->R, accR, sizeof(accR));
+        memcpy(st->t, acct, sizeof(acct));
+        memcpy(st->axis, jd->axis, sizeof(st->axis));
+        double x = jd->axis[0], y = jd->axis[1], z = jd->axis[2];
+        st->axis_sq[0] = x * x; st->axis_sq[1] = y * y; st->axis_sq[2] = z * z;
+        st->axis_sq[3] = x * y; st->axis_sq[4] = x * z; st->axis_sq[5] = y * z;
+        st->sign = 1.0;
+        if (jd->type == ORC_JOINT_PRISMATIC) {
+            st->kind = ORC_STEP_PRISMATIC;
+        } else if (jd->type == ORC_JOINT_REVOLUTE) {
+            st->kind = ORC_STEP_REV_GENERAL;
+            if (fabs(x) == 1.0 && y == 0.0 && z == 0.0) { st->kind = ORC_STEP_REV_X; st->sign = x; }
+            if (x == 0.0 && fabs(y) == 1.0 && z == 0.0) { st->kind = ORC_STEP_REV_Y; st->sign = y; }
+            if (x == 0.0 && y == 0.0 && fabs(z) == 1.0) { st->kind = ORC_STEP_REV_Z; st->sign = z; }
+        } else {
+            return -2;
+        }
+        /* Robot::from, robot.cpp:52-72 */
+        orc_variable* v = &out->vars[n];
+        v->bounded = jd->bounded;
+        v->min = jd->min_position;
+        v->max = jd->max_position;
+        v->mid = 0.5 * (v->min + v->max);
+        v->half_span = v->bounded ? (v->max - v->min) / 2.0 : M_PI;
+        v->max_velocity_rcp = jd->max_velocity > 0.0 ? 1.0 / jd->max_velocity : 0.0;
+        ++n;
+        have_acc = 0;
+    }
+    out->n = n;
+    out->has_tip = have_acc;
+    if (have_acc) {
+        memcpy(out->tip_R, accR, sizeof(accR));
+        memcpy(out->tip_t, acct, sizeof(acct));
+    }
+    /* robot.cpp:69-82 */
+    double divisor = 0.0;
+    for (int i = 0; i < n; ++i) {
+        out->vars[i].minimal_displacement_factor = 1.0 / (double)n;
+        divisor += out->vars[i].max_velocity_rcp;
+    }
+    if (divisor > 0.0)
+        for (int i = 0; i < n; ++i)
+            out->vars[i].minimal_displacement_factor = out->vars[i].max_velocity_rcp / divisor;
+    return n > 0 ? 0 : -3;
+}
+
+/* Rotate columns (a, b) of R: the product R * Rot_axis(angle) for an axis-aligned joint.
+ * col_a' = col_a * c + col_b * s ; col_b' = col_b * c - col_a * s */
+static void rotate_cols(double R[9], int a, int b, double s, double c) {
+    for (int r = 0; r < 3; ++r) {
+        double va = R[3 * r + a], vb = R[3 * r + b];
+        R[3 * r + a] = fma(vb, s, va * c);
+        R[3 * r + b] = fma(vb, c, -(va * s));
+    }
+}
+
+/* One moving joint applied to frame (R, t) that already includes the folded origin.
+ * Revolute: RevoluteJointModel::computeTransform (same rotation as
+ * forward_kinematics.cpp:48-57); prismatic: forward_kinematics.cpp:58-63. */
+static void apply_joint(const orc_step* st, double q, double R[9], double t[3]) {
+    if (st->kind == ORC_STEP_PRISMATIC) {
+        double d[3] = {st->axis[0] * q, st->axis[1] * q, st->axis[2] * q};
+        double nt[3];
+        mat_vec_add(R, d, t, nt);
+        t[0] = nt[0]; t[1] = nt[1]; t[2] = nt[2];
+        return;
+    }
+    double s, c;
+    orc_sincos(q, &s, &c);
+    switch (st->kind) {
+        case ORC_STEP_REV_X: rotate_cols(R, 1, 2, st->sign * s, c); break;
+        case ORC_STEP_REV_Y: rotate_cols(R, 2, 0, st->sign * s, c); break;
+        case ORC_STEP_REV_Z: rotate_cols(R, 0, 1, st->sign * s, c); break;
+        default: {
+            double x = st->axis[0], y = st->axis[1], z = st->axis[2];
+            const double* a2 = st->axis_sq;
+            double t1 = 1.0 - c;
+            double J[9], N[9];
+            J[0] = fma(t1, a2[0], c);
+            J[1] = fma(t1, a2[3], -(z * s));
+            J[2] = fma(t1, a2[4], y * s);
+            J[3] = fma(t1, a2[3], z * s);
+            J[4] = fma(t1, a2[1], c);
+            J[5] = fma(t1, a2[5], -(x * s));
+            J[6] = fma(t1, a2[4], -(y * s));
+            J[7] = fma(t1, a2[5], x * s);
+            J[8] = fma(t1, a2[2], c);
+            mat_mul(R, J, N);
+            memcpy(R, N, sizeof(N));
+        }
+    }
+}
+
+/* fk_moveit.cpp:20-34 -> tip frame of the chain.  Chain walk left to right. */
+void orc_fk(const orc_robot* robot, const double* q, double R[9], double t[3]) {
+    memcpy(R, robot->steps[0].R, 9 * sizeof(double));
+    memcpy(t, robot->steps[0].t, 3 * sizeof(double));
+    apply_joint(&robot->steps[0], q[0], R, t);
+    for (int j = 1; j < robot->n; ++j) {
+        const orc_step* st = &robot->steps[j];
+        double nR[9], nt[3];
+        mat_vec_add(R, st->t, t, nt);
+        mat_mul(R, st->R, nR);
+        memcpy(R, nR, sizeof(nR));
+        memcpy(t, nt, sizeof(nt));
+        apply_joint(st, q[j], R, t);
+    }
+    if (robot->has_tip) {
+        double nR[9], nt[3];
+        mat_vec_add(R, robot->tip_t, t, nt);
+        mat_mul(R, robot->tip_R, nR);
+        memcpy(R, nR, sizeof(nR));
+        memcpy(t, nt, sizeof(nt));
+    }
+}
+
+/* robot.cpp:36-42 (std::clamp(v, lo, hi) = v < lo ? lo : hi < v ? hi : v) */
+double orc_clamp_to_limits(const orc_variable* v, double val) {
+    double lo = v->bounded ? v->min : val - v->half_span;
+    double hi = v->bounded ? v->max : val + v->half_span;
+    return (val < lo) ? lo : ((hi < val) ? hi : val);
+}
+
+/* robot.cpp:32-34, 97-105 */
+int orc_is_valid_configuration(const orc_robot* robot, const double* q) {
+    for (int i = 0; i < robot->n; ++i) {
+        const orc_variable* v = &robot->vars[i];
+        if (!(!v->bounded || (q[i] <= v->max && q[i] >= v->min))) return 0;
+    }
+    return 1;
+}
+
+/* robot.cpp:23-30, 87-95 */
+static void set_random_valid_configuration(const orc_robot* robot, orc_rng* rng, double* config) {
+    for (int i = 0; i < robot->n; ++i) {
+        const orc_variable* v = &robot->vars[i];
+        if (v->bounded)
+            config[i] = rng_uniform_real(rng, v->min, v->max);
+        else
+            config[i] = rng_uniform_real(rng, config[i] - M_PI, config[i] + M_PI);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Goals, cost, solution test
+ * ------------------------------------------------------------------------------------------ */
+void orc_params_default(orc_params* p) {
+    /* src/pick_ik_parameters.yaml defaults */
+    memset(p, 0, sizeof(*p));
+    p->mode = 0;
+    p->gd_step_size = 0.0001;
+    p->gd_max_iters = 100;
+    p->gd_min_cost_delta = 1.0e-12;
+    p->position_threshold = 0.001;
+    p->orientation_threshold = 0.001;
+    p->cost_threshold = 0.001;
+    p->position_scale = 1.0;
+    p->rotation_scale = 0.5;
+    p->center_joints_weight = 0.0;
+    p->avoid_joint_limits_weight = 0.0;
+    p->minimal_displacement_weight = 0.0;
+    p->stop_optimization_on_valid_solution = 1;
+    p->memetic_population_size = 16;
+    p->memetic_elite_size = 4;
+    p->memetic_wipeout_fitness_tol = 0.00001;
+    p->memetic_max_generations = 100;
+    p->memetic_gd_max_iters = 25;
+    p->return_approximate_solution = 0;
+    p->rng_seed = 0x5EED;
+}
+
+void orc_problem_init(orc_problem* pb, const orc_robot* robot, const orc_params* params,
+                      const double goal_pose[7], const double* seed) {
+    pb->robot = robot;
+    pb->params = params;
+    pb->goal_t[0] = goal_pose[0];
+    pb->goal_t[1] = goal_pose[1];
+    pb->goal_t[2] = goal_pose[2];
+    orc_quat_to_matrix(goal_pose + 3, pb->goal_R);     /* tf2::fromMsg, robot.cpp:175-176 */
+    orc_matrix_to_quat(pb->goal_R, pb->goal_q);        /* goal.cpp:22 */
+    for (int i = 0; i < ORC_MAX_VARS; ++i) pb->seed[i] = (i < robot->n) ? seed[i] : 0.0;
+}
+
+/* goal.cpp:91-108 */
+double orc_center_joints_cost(const orc_robot* robot, const double* q) {
+    double sum = 0.0;
+    for (int i = 0; i < robot->n; ++i) {
+        const orc_variable* v = &robot->vars[i];
+        if (!v->bounded) continue;
+        double mid = (v->min + v->max) * 0.5;
+        double e = (q[i] - mid) * v->minimal_displacement_factor;
+        sum += e * e;
+    }
+    return sum;
+}
+
+/* goal.cpp:110-129 */
+double orc_avoid_joint_limits_cost(const orc_robot* robot, const double* q) {
+    double sum = 0.0;
+    for (int i = 0; i < robot->n; ++i) {
+        const orc_variable* v = &robot->vars[i];
+        if (!v->bounded) continue;
+        double x = fabs(q[i] - v->mid) * 2.0 - v->half_span;
+        double m = (x > 0.0) ? x : 0.0; /* std::fmax(0.0, x): NaN -> 0 */
+        double e = m * v->minimal_displacement_factor;
+        sum += e * e;
+    }
+    return sum;
+}
+
+/* goal.cpp:131-144 */
+double orc_minimal_displacement_cost(const orc_robot* robot, const double* q, const double* seed) {
+    double sum = 0.0;
+    for (int i = 0; i < robot->n; ++i) {
+        double e = (q[i] - seed[i]) * robot->vars[i].minimal_displacement_factor;
+        sum += e * e;
+    }
+    return sum;
+}
+
+/* goals in plugin order (pick_ik_plugin.cpp:118-129); returns count, fills weighted costs */
+static int goal_costs(const orc_problem* pb, const double* q, double out[3]) {
+    const orc_params* p = pb->params;
+    int n = 0;
+    if (p->center_joints_weight > 0.0)
+        out[n++] = orc_center_joints_cost(pb->robot, q) * (p->center_joints_weight * p->center_joints_weight);
+    if (p->avoid_joint_limits_weight > 0.0)
+        out[n++] = orc_avoid_joint_limits_cost(pb->robot, q) *
+                   (p->avoid_joint_limits_weight * p->avoid_joint_limits_weight);
+    if (p->minimal_displacement_weight > 0.0)
+        out[n++] = orc_minimal_displacement_cost(pb->robot, q, pb->seed) *
+                   (p->minimal_displacement_weight * p->minimal_displacement_weight);
+    return n;
+}
+
+/* goal.cpp:188-203 */
+double orc_cost(const orc_problem* pb, const double* q) {
+    double R[9], t[3];
+    orc_fk(pb->robot, q, R, t);
+    double pose_cost = 0.0 + pose_cost_q(pb->goal_t, pb->goal_q, t, R, pb->params->position_scale,
+                                         pb->params->rotation_scale);
+    double g[3];
+    int ng = goal_costs(pb, q, g);
+    double goal_cost = 0.0;
+    for (int i = 0; i < ng; ++i) goal_cost = goal_cost + g[i];
+    return pose_cost + goal_cost;
+}
+
+/* goal.cpp:163-186 with thresholds enabled as pick_ik_plugin.cpp:97-106 */
+int orc_is_solution(const orc_problem* pb, const double* q) {
+    const orc_params* p = pb->params;
+    double R[9], t[3];
+    orc_fk(pb->robot, q, R, t);
+    if (p->position_scale > 0.0 && !(orc_linear_distance(pb->goal_t, t) <= p->position_threshold))
+        return 0;
+    if (p->rotation_scale > 0.0 &&
+        !(fabs(orc_angular_distance_q(pb->goal_q, R)) <= p->orientation_threshold))
+        return 0;
+    double thr_sq = p->cost_threshold * p->cost_threshold;
+    double g[3];
+    int ng = goal_costs(pb, q, g);
+    for (int i = 0; i < ng; ++i)
+        if (g[i] >= thr_sq) return 0;
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Gradient descent (src/ik_gradient.cpp)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const orc_problem* pb;
+    uint64_t evals;
+    uint32_t gd_steps;
+} orc_ctx;
+
+static double cost_counted(orc_ctx* cx, const double* q) {
+    cx->evals++;
+    return orc_cost(cx->pb, q);
+}
+
+/* ik_gradient.cpp:24-94 */
+static int gd_step(orc_ctx* cx, double* gradient, double* working, double* local, double* best,
+                   double* local_cost, double* best_cost) {
+    const orc_robot* robot = cx->pb->robot;
+    const double step_size = cx->pb->params->gd_step_size;
+    const int n = robot->n;
+    cx->gd_steps++;
+    for (int i = 0; i < n; ++i) {
+        working[i] = local[i] - step_size;
+        double p1 = cost_counted(cx, working);
+        working[i] = local[i] + step_size;
+        double p3 = cost_counted(cx, working);
+        working[i] = local[i];
+        gradient[i] = p3 - p1;
+    }
+    double sum = step_size;
+    for (int i = 0; i < n; ++i) sum = sum + fabs(gradient[i]);
+    double f = 1.0 / sum * step_size;
+    for (int i = 0; i < n; ++i) gradient[i] = gradient[i] * f;
+
+    for (int i = 0; i < n; ++i) working[i] = local[i] - gradient[i];
+    double p1 = cost_counted(cx, working);
+    for (int i = 0; i < n; ++i) working[i] = local[i] + gradient[i];
+    double p3 = cost_counted(cx, working);
+    double p2 = (p1 + p3) * 0.5;
+    double cost_diff = (p3 - p1) * 0.5;
+    double joint_diff = p2 / cost_diff;
+    if (!isfinite(joint_diff)) joint_diff = 0.0;
+
+    for (int i = 0; i < n; ++i) {
+        double updated = local[i] - gradient[i] * joint_diff;
+        working[i] = orc_clamp_to_limits(&robot->vars[i], updated);
+    }
+    for (int i = 0; i < n; ++i) local[i] = working[i];
+    *local_cost = cost_counted(cx, local);
+    if (*local_cost < *best_cost) {
+        for (int i = 0; i < n; ++i) best[i] = local[i];
+        *best_cost = *local_cost;
+        return 1;
+    }
+    return 0;
+}
+
+int orc_gd_step(const orc_problem* pb, double* gradient, double* working, double* local,
+                double* best, double* local_cost, double* best_cost) {
+    orc_ctx cx = {pb, 0, 0};
+    return gd_step(&cx, gradient, working, local, best, local_cost, best_cost);
+}
+
+/* ik_gradient.cpp:96-139, max_time = inf */
+void orc_ik_gradient(const orc_problem* pb, const double* initial_guess, orc_result* out) {
+    const orc_params* p = pb->params;
+    const int n = pb->robot->n;
+    memset(out, 0, sizeof(*out));
+    orc_ctx cx = {pb, 0, 0};
+    if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, initial_guess)) {
+        out->found = 1;
+        memcpy(out->solution, initial_guess, n * sizeof(double));
+        out->cost = orc_cost(pb, initial_guess);
+        return;
+    }
+    double gradient[ORC_MAX_VARS] = {0}, working[ORC_MAX_VARS], local[ORC_MAX_VARS], best[ORC_MAX_VARS];
+    double local_cost = cost_counted(&cx, initial_guess), best_cost = local_cost;
+    for (int i = 0; i < n; ++i) working[i] = local[i] = best[i] = initial_guess[i];
+
+    int num_iterations = 0, found = 0;
+    double previous_cost = 0.0;
+    while (num_iterations < p->gd_max_iters) {
+        if (gd_step(&cx, gradient, working, local, best, &local_cost, &best_cost)) {
+            if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, best)) {
+                found = 1;
+                break;
+            }
+        }
+        if (fabs(local_cost - previous_cost) <= p->gd_min_cost_delta) break;
+        previous_cost = local_cost;
+        num_iterations++;
+    }
+    if (!found && !p->stop_optimization_on_valid_solution && orc_is_solution(pb, best)) found = 1;
+    if (!found && p->return_approximate_solution) found = 1;
+    out->found = found;
+    out->iterations = num_iterations;
+    out->cost = best_cost;
+    out->evals = cx.evals;
+    out->gd_steps = cx.gd_steps;
+    memcpy(out->solution, best, n * sizeof(double));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Memetic solver (src/ik_memetic.cpp), single species, max_time = inf
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    double genes[ORC_MAX_VARS];
+    double gradient[ORC_MAX_VARS];
+    double fitness;
+    double extinction;
+} orc_individual;
+
+typedef struct {
+    orc_ctx cx;
+    int n, P, E;
+    uint32_t problem_index;
+    orc_individual* pop;
+    orc_individual* scratch;
+    int* order;
+    orc_individual best, best_curr;
+    int has_previous;
+    double previous_fitness;
+    uint32_t init_epoch;
+    uint32_t wipeouts;
+} orc_memetic;
+
+/* ik_memetic.cpp:57-64 */
+static void compute_extinctions(orc_memetic* m) {
+    double min_fitness = m->pop[0].fitness;
+    double max_fitness = m->pop[m->P - 1].fitness;
+    for (int i = 0; i < m->P; ++i) {
+        double grading = (double)i / (double)(m->P - 1); /* ik_memetic.cpp:36-39 */
+        m->pop[i].extinction = (m->pop[i].fitness + min_fitness * (grading - 1.0)) / max_fitness;
+    }
+}
+
+/* ik_memetic.cpp:93-117.  RNG stream: (STREAM_INIT, epoch, elite index). */
+static void init_population(orc_memetic* m, const double* initial_guess) {
+    const orc_robot* robot = m->cx.pb->robot;
+    for (int i = 0; i < m->E; ++i) {
+        orc_individual* ind = &m->pop[i];
+        memset(ind, 0, sizeof(*ind));
+        memcpy(ind->genes, initial_guess, m->n * sizeof(double));
+        if (i > 0) {
+            orc_rng rng;
+            rng_init(&rng, m->cx.pb->params->rng_seed, m->problem_index, STREAM_INIT, m->init_epoch,
+                     (uint32_t)i);
+            set_random_valid_configuration(robot, &rng, ind->genes);
+        }
+        ind->fitness = cost_counted(&m->cx, ind->genes);
+        ind->extinction = 1.0;
+    }
+    for (int i = m->E; i < m->P; ++i) {
+        orc_individual* ind = &m->pop[i];
+        memset(ind, 0, sizeof(*ind));
+        memcpy(ind->genes, initial_guess, m->n * sizeof(double));
+        ind->extinction = 1.0;
+    }
+    for (int i = 0; i < m->P; ++i) m->pop[i].fitness = cost_counted(&m->cx, m->pop[i].genes);
+    compute_extinctions(m);
+    m->has_previous = 0;
+    m->init_epoch++;
+}
+
+/* ik_memetic.cpp:66-91 */
+static void gradient_descent(orc_memetic* m, int i) {
+    const orc_params* p = m->cx.pb->params;
+    orc_individual* ind = &m->pop[i];
+    const int n = m->n;
+    double gradient[ORC_MAX_VARS] = {0}, working[ORC_MAX_VARS], local[ORC_MAX_VARS], best[ORC_MAX_VARS];
+    double local_cost = cost_counted(&m->cx, ind->genes), best_cost = local_cost;
+    for (int k = 0; k < n; ++k) working[k] = local[k] = best[k] = ind->genes[k];
+    int num_iterations = 0;
+    double previous_cost = 0.0;
+    while (num_iterations < p->memetic_gd_max_iters) {
+        gd_step(&m->cx, gradient, working, local, best, &local_cost, &best_cost);
+        if (fabs(local_cost - previous_cost) <= p->gd_min_cost_delta) break;
+        previous_cost = local_cost;
+        num_iterations++;
+    }
+    for (int k = 0; k < n; ++k) ind->genes[k] = best[k];
+    ind->fitness = cost_counted(&m->cx, ind->genes);
+    for (int k = 0; k < n; ++k) ind->gradient[k] = gradient[k];
+}
+
+/* ik_memetic.cpp:119-190.  RNG stream per child: (STREAM_REPRODUCE, generation, child index);
+ * draw order: idxA, idxB (rejection loop), mix, then per gene r_A, r_B, r_mut, [r_amp]. */
+static void reproduce(orc_memetic* m, uint32_t generation) {
+    const orc_robot* robot = m->cx.pb->robot;
+    const int n = m->n;
+    const double inverse_gene_size = 1.0 / (double)n;
+    int pool[ORC_MAX_VARS * 64];
+    int pool_size = m->E;
+    for (int i = 0; i < m->E; ++i) pool[i] = i;
+
+    for (int i = m->E; i < m->P; ++i) {
+        orc_individual* child = &m->pop[i];
+        orc_rng rng;
+        rng_init(&rng, m->cx.pb->params->rng_seed, m->problem_index, STREAM_REPRODUCE, generation,
+                 (uint32_t)i);
+        if (pool_size > 0) {
+            uint32_t idxA = rng_uniform_int(&rng, (uint32_t)pool_size);
+            uint32_t idxB = idxA;
+            while (idxB == idxA && pool_size > 1) idxB = rng_uniform_int(&rng, (uint32_t)pool_size);
+            const int ia = pool[idxA], ib = pool[idxB];
+            const orc_individual* parentA = &m->pop[ia];
+            const orc_individual* parentB = &m->pop[ib];
+
+            double extinction = 0.5 * (parentA->extinction + parentB->extinction);
+            double mutation_prob = extinction * (1.0 - inverse_gene_size) + inverse_gene_size;
+            double mix_ratio = rng_uniform_real(&rng, 0.0, 1.0);
+            for (int j = 0; j < n; ++j) {
+                const orc_variable* joint = &robot->vars[j];
+                double gene = mix_ratio * parentA->genes[j] + (1.0 - mix_ratio) * parentB->genes[j];
+                double rA = rng_uniform_real(&rng, 0.0, 1.0);
+                double rB = rng_uniform_real(&rng, 0.0, 1.0);
+                gene += rA * parentA->gradient[j] + rB * parentB->gradient[j];
+                double original_gene = gene;
+                if (rng_uniform_real(&rng, 0.0, 1.0) < mutation_prob)
+                    gene += extinction * joint->half_span * rng_uniform_real(&rng, -1.0, 1.0);
+                gene = orc_clamp_to_limits(joint, gene);
+                child->genes[j] = gene;
+                child->gradient[j] = gene - original_gene;
+            }
+            child->fitness = cost_counted(&m->cx, child->genes);
+            /* parents referenced by identity; A first, then B */
+            if (child->fitness < parentA->fitness) {
+                for (int k = 0; k < pool_size; ++k)
+                    if (pool[k] == ia) {
+                        for (int l = k; l + 1 < pool_size; ++l) pool[l] = pool[l + 1];
+                        pool_size--;
+                        break;
+                    }
+            }
+            if (child->fitness < parentB->fitness) {
+                for (int k = 0; k < pool_size; ++k)
+                    if (pool[k] == ib) {
+                        for (int l = k; l + 1 < pool_size; ++l) pool[l] = pool[l + 1];
+                        pool_size--;
+                        break;
+                    }
+            }
+        } else {
+            set_random_valid_configuration(robot, &rng, child->genes);
+            child->fitness = cost_counted(&m->cx, child->genes);
+            for (int j = 0; j < n; ++j) child->gradient[j] = 0.0;
+        }
+    }
+}
+
+/* NaN sorts last; ties keep pre-sort order (the reference's std::sort is unstable: defined here) */
+static int fit_less(double a, double b) {
+    if (a != a) return 0;
+    if (b != b) return 1;
+    return a < b;
+}
+
+/* ik_memetic.cpp:200-209 */
+static void sort_population(orc_memetic* m) {
+    for (int i = 0; i < m->P; ++i) m->order[i] = i;
+    for (int i = 1; i < m->P; ++i) { /* stable insertion sort on indices */
+        int oi = m->order[i];
+        double f = m->pop[oi].fitness;
+        int k = i;
+        while (k > 0 && fit_less(f, m->pop[m->order[k - 1]].fitness)) {
+            m->order[k] = m->order[k - 1];
+            --k;
+        }
+        m->order[k] = oi;
+    }
+    for (int i = 0; i < m->P; ++i) m->scratch[i] = m->pop[m->order[i]];
+    memcpy(m->pop, m->scratch, (size_t)m->P * sizeof(orc_individual));
+    compute_extinctions(m);
+    m->best_curr = m->pop[0];
+    if (m->best_curr.fitness < m->best.fitness) m->best = m->best_curr;
+}
+
+/* ik_memetic.cpp:43-55 */
+static int check_wipeout(orc_memetic* m) {
+    if (m->has_previous) {
+        int improved = m->best_curr.fitness <
+                       m->previous_fitness - m->cx.pb->params->memetic_wipeout_fitness_tol;
+        if (!improved) return 1;
+    }
+    m->has_previous = 1;
+    m->previous_fitness = m->best_curr.fitness;
+    return 0;
+}
+
+/* ik_memetic.cpp:285-296 + 211-283 */
+void orc_ik_memetic(const orc_problem* pb, const double* initial_guess, uint32_t problem_index,
+                    orc_result* out) {
+    const orc_params* p = pb->params;
+    const int n = pb->robot->n;
+    memset(out, 0, sizeof(*out));
+    if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, initial_guess)) {
+        out->found = 1;
+        memcpy(out->solution, initial_guess, n * sizeof(double));
+        out->cost = orc_cost(pb, initial_guess);
+        return;
+    }
+    orc_memetic m;
+    memset(&m, 0, sizeof(m));
+    m.cx.pb = pb;
+    m.n = n;
+    m.P = p->memetic_population_size;
+    m.E = p->memetic_elite_size;
+    m.problem_index = problem_index;
+    m.pop = (orc_individual*)calloc((size_t)m.P, sizeof(orc_individual));
+    m.scratch = (orc_individual*)calloc((size_t)m.P, sizeof(orc_individual));
+    m.order = (int*)calloc((size_t)m.P, sizeof(int));
+
+    /* MemeticIk::from, ik_memetic.cpp:18-41 */
+    memset(&m.best, 0, sizeof(m.best));
+    memcpy(m.best.genes, initial_guess, n * sizeof(double));
+    m.best.fitness = cost_counted(&m.cx, initial_guess);
+    m.best_curr = m.best;
+
+    init_population(&m, initial_guess);
+
+    int iter = 0, found = 0;
+    while (iter < p->memetic_max_generations) {
+        for (int i = 0; i < m.E; ++i) gradient_descent(&m, i);
+        reproduce(&m, (uint32_t)iter);
+        sort_population(&m);
+        if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, m.best.genes)) {
+            found = 1;
+            break;
+        }
+        if (check_wipeout(&m)) {
+            m.wipeouts++;
+            init_population(&m, m.best.genes);
+        }
+        iter++;
+    }
+    if (!found && !p->stop_optimization_on_valid_solution && orc_is_solution(pb, m.best.genes)) found = 1;
+    if (!found && p->return_approximate_solution) found = 1;
+
+    out->found = found;
+    out->iterations = iter;
+    out->cost = m.best.fitness;
+    out->evals = m.cx.evals;
+    out->wipeouts = m.wipeouts;
+    out->gd_steps = m.cx.gd_steps;
+    memcpy(out->solution, m.best.genes, n * sizeof(double));
+    free(m.pop);
+    free(m.scratch);
+    free(m.order);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Batch drivers
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const orc_robot* robot;
+    const orc_params* params;
+    int64_t B, first;
+    const double* goal_pose;
+    const double* seed;
+    int64_t seed_stride;
+    double* solution;
+    int32_t* error_code;
+    double* cost;
+    int32_t* iterations;
+    uint64_t evals;
+    int64_t next; /* atomic work counter */
+    pthread_mutex_t mu;
+} batch_job;
+
+static void solve_one(batch_job* job, int64_t b, uint64_t* evals) {
+    const int n = job->robot->n;
+    const double* seed = job->seed + b * job->seed_stride;
+    orc_problem pb;
+    orc_problem_init(&pb, job->robot, job->params, job->goal_pose + 7 * b, seed);
+    orc_result res;
+    if (job->params->mode == 0)
+        orc_ik_memetic(&pb, seed, (uint32_t)(job->first + b), &res);
+    else
+        orc_ik_gradient(&pb, seed, &res);
+    /* pick_ik_plugin.cpp:209-217 */
+    if (res.found) {
+        job->error_code[b] = 1;
+        memcpy(job->solution + b * n, res.solution, n * sizeof(double));
+    } else {
+        job->error_code[b] = -31;
+        memcpy(job->solution + b * n, seed, n * sizeof(double));
+    }
+    if (job->cost) job->cost[b] = res.cost;
+    if (job->iterations) job->iterations[b] = res.iterations;
+    *evals += res.evals;
+}
+
+static void* batch_worker(void* arg) {
+    batch_job* job = (batch_job*)arg;
+    uint64_t evals = 0;
+    for (;;) {
+        int64_t b = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
+        if (b >= job->B) break;
+        solve_one(job, b, &evals);
+    }
+    pthread_mutex_lock(&job->mu);
+    job->evals += evals;
+    pthread_mutex_unlock(&job->mu);
+    return NULL;
+}
+
+void orc_solve_batch(const orc_robot* robot, const orc_params* params, int64_t B,
+                     int64_t first_problem_index, const double* goal_pose, const double* seed,
+                     int64_t seed_stride, double* solution, int32_t* error_code, double* cost,
+                     int32_t* iterations, uint64_t* evals_total, int n_threads) {
+    batch_job job;
+    memset(&job, 0, sizeof(job));
+    job.robot = robot; job.params = params; job.B = B; job.first = first_problem_index;
+    job.goal_pose = goal_pose; job.seed = seed; job.seed_stride = seed_stride;
+    job.solution = solution; job.error_code = error_code; job.cost = cost; job.iterations = iterations;
+    pthread_mutex_init(&job.mu, NULL);
+    if (n_threads <= 0) n_threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (n_threads > B) n_threads = (int)(B > 0 ? B : 1);
+    if (n_threads <= 1) {
+        batch_worker(&job);
+    } else {
+        pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+        for (int i = 0; i < n_threads; ++i) pthread_create(&th[i], NULL, batch_worker, &job);
+        for (int i = 0; i < n_threads; ++i) pthread_join(th[i], NULL);
+        free(th);
+    }
+    pthread_mutex_destroy(&job.mu);
+    if (evals_total) *evals_total = job.evals;
+}
+
+void orc_eval_cost_batch(const orc_robot* robot, const orc_params* params, int64_t B,
+                         const double* goal_pose, const double* seed, int64_t seed_stride,
+                         const double* q, double* cost, int32_t* is_solution, double* tip_pose) {
+    const int n = robot->n;
+    for (int64_t b = 0; b < B; ++b) {
+        orc_problem pb;
+        orc_problem_init(&pb, robot, params, goal_pose + 7 * b, seed + b * seed_stride);
+        if (cost) cost[b] = orc_cost(&pb, q + b * n);
+        if (is_solution) is_solution[b] = orc_is_solution(&pb, q + b * n);
+        if (tip_pose) {
+            double R[9], t[3];
+            orc_fk(robot, q + b * n, R, t);
+            tip_pose[7 * b + 0] = t[0]; tip_pose[7 * b + 1] = t[1]; tip_pose[7 * b + 2] = t[2];
+            orc_matrix_to_quat(R, tip_pose + 7 * b + 3);
+        }
+    }
+}
+
+/* SURVEY 8(d) synthetic inputs: q* ~ U(min, max) per variable (unbounded: U(-pi, pi)) */
+void orc_random_configuration(const orc_robot* robot, uint64_t gen_seed, uint32_t problem_index,
+                              double* q) {
+    orc_rng rng;
+    rng_init(&rng, gen_seed, problem_index, STREAM_TARGET, 0, 0);
+    for (int i = 0; i < robot->n; ++i) {
+        const orc_variable* v = &robot->vars[i];
+        q[i] = v->bounded ? rng_uniform_real(&rng, v->min, v->max) : rng_uniform_real(&rng, -M_PI, M_PI);
+    }
+}
+
+void orc_pose_from_fk(const orc_robot* robot, const double* q, double pose[7]) {
+    double R[9], t[3];
+    orc_fk(robot, q, R, t);
+    pose[0] = t[0]; pose[1] = t[1]; pose[2] = t[2];
+    orc_matrix_to_quat(R, pose + 3);
+}

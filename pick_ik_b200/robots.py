@@ -1,0 +1,214 @@
+"""Robot chain fixtures for the batched IK engine.
+
+Each robot is a serial chain of joints from the model root to the tip link, in the layout of
+``pik_joint_desc`` (include/pik.h).  The reference gets the same information from a MoveIt
+``RobotModel`` (``Robot::from``, /root/reference/src/robot.cpp:44-85 and
+``get_active_variable_indices``, robot.cpp:122-160); there is no MoveIt/URDF here, so the
+chains of the robots the reference's tests and BASELINE.json's configs name are tabulated
+(SURVEY.md Appendix C).
+
+rpy -> rotation follows urdfdom ``Rotation::setFromRPY`` (quaternion, normalised) and Eigen
+``Quaterniond::toRotationMatrix`` as MoveIt does when it builds joint origin transforms
+(SURVEY.md Appendix B.3).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+
+JOINT_FIXED = 0
+JOINT_REVOLUTE = 1
+JOINT_PRISMATIC = 2
+
+# numpy mirror of pik_joint_desc / orc_joint_desc (natural C alignment, 176 bytes)
+JOINT_DESC_DTYPE = np.dtype(
+    [
+        ("type", np.int32),
+        ("bounded", np.int32),
+        ("origin_R", np.float64, (9,)),
+        ("origin_t", np.float64, (3,)),
+        ("axis", np.float64, (3,)),
+        ("min_position", np.float64),
+        ("max_position", np.float64),
+        ("max_velocity", np.float64),
+    ],
+    align=True,
+)
+
+
+def rpy_to_matrix(r: float, p: float, y: float) -> np.ndarray:
+    """urdfdom setFromRPY -> quaternion -> Eigen toRotationMatrix (row-major 3x3)."""
+    phi, the, psi = r / 2.0, p / 2.0, y / 2.0
+    qx = math.sin(phi) * math.cos(the) * math.cos(psi) - math.cos(phi) * math.sin(the) * math.sin(psi)
+    qy = math.cos(phi) * math.sin(the) * math.cos(psi) + math.sin(phi) * math.cos(the) * math.sin(psi)
+    qz = math.cos(phi) * math.cos(the) * math.sin(psi) - math.sin(phi) * math.sin(the) * math.cos(psi)
+    qw = math.cos(phi) * math.cos(the) * math.cos(psi) + math.sin(phi) * math.sin(the) * math.sin(psi)
+    nrm = math.sqrt(qx * qx + qy * qy + qz * qz + qw * qw)
+    qx, qy, qz, qw = qx / nrm, qy / nrm, qz / nrm, qw / nrm
+    return quat_to_matrix(qw, qx, qy, qz)
+
+
+def quat_to_matrix(w: float, x: float, y: float, z: float) -> np.ndarray:
+    tx, ty, tz = 2.0 * x, 2.0 * y, 2.0 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    return np.array(
+        [
+            [1.0 - (tyy + tzz), txy - twz, txz + twy],
+            [txy + twz, 1.0 - (txx + tzz), tyz - twx],
+            [txz - twy, tyz + twx, 1.0 - (txx + tyy)],
+        ],
+        dtype=np.float64,
+    )
+
+
+@dataclass
+class Joint:
+    name: str
+    type: int
+    xyz: Sequence[float] = (0.0, 0.0, 0.0)
+    rpy: Sequence[float] = (0.0, 0.0, 0.0)
+    axis: Sequence[float] = (0.0, 0.0, 1.0)
+    lower: float = 0.0
+    upper: float = 0.0
+    velocity: float = 0.0
+    continuous: bool = False  # URDF "continuous": position_bounded_ = false, bounds -pi..pi
+
+
+@dataclass
+class RobotChain:
+    name: str
+    base_link: str
+    tip_link: str
+    joints: List[Joint] = field(default_factory=list)
+
+    @property
+    def variable_names(self) -> List[str]:
+        return [j.name for j in self.joints if j.type != JOINT_FIXED]
+
+    @property
+    def num_variables(self) -> int:
+        return len(self.variable_names)
+
+    def joint_desc(self) -> np.ndarray:
+        out = np.zeros(len(self.joints), dtype=JOINT_DESC_DTYPE)
+        for i, j in enumerate(self.joints):
+            out[i]["type"] = j.type
+            out[i]["origin_R"] = rpy_to_matrix(*j.rpy).reshape(9)
+            out[i]["origin_t"] = np.asarray(j.xyz, dtype=np.float64)
+            ax = np.asarray(j.axis, dtype=np.float64)
+            if j.type != JOINT_FIXED:
+                ax = ax / math.sqrt(float(ax @ ax))  # RevoluteJointModel::setAxis normalises
+            out[i]["axis"] = ax
+            if j.type == JOINT_FIXED:
+                continue
+            if j.continuous:
+                out[i]["bounded"] = 0
+                out[i]["min_position"] = -math.pi
+                out[i]["max_position"] = math.pi
+            else:
+                out[i]["bounded"] = 1
+                out[i]["min_position"] = j.lower
+                out[i]["max_position"] = j.upper
+            out[i]["max_velocity"] = abs(j.velocity)
+        return out
+
+
+H = 1.57079632679  # the literal the URDFs carry
+
+
+def panda(tip: str = "panda_hand") -> RobotChain:
+    """Franka Panda, group panda_arm (moveit_resources_panda_description/urdf/panda.urdf)."""
+    R, F = JOINT_REVOLUTE, JOINT_FIXED
+    joints = [
+        Joint("panda_joint1", R, (0, 0, 0.333), (0, 0, 0), (0, 0, 1), -2.8973, 2.8973, 2.1750),
+        Joint("panda_joint2", R, (0, 0, 0), (-H, 0, 0), (0, 0, 1), -1.7628, 1.7628, 2.1750),
+        Joint("panda_joint3", R, (0, -0.316, 0), (H, 0, 0), (0, 0, 1), -2.8973, 2.8973, 2.1750),
+        Joint("panda_joint4", R, (0.0825, 0, 0), (H, 0, 0), (0, 0, 1), -3.0718, -0.0698, 2.1750),
+        Joint("panda_joint5", R, (-0.0825, 0.384, 0), (-H, 0, 0), (0, 0, 1), -2.8973, 2.8973, 2.6100),
+        Joint("panda_joint6", R, (0, 0, 0), (H, 0, 0), (0, 0, 1), -0.0175, 3.7525, 2.6100),
+        Joint("panda_joint7", R, (0.088, 0, 0), (H, 0, 0), (0, 0, 1), -2.8973, 2.8973, 2.6100),
+        Joint("panda_joint8", F, (0, 0, 0.107)),
+    ]
+    if tip == "panda_hand":
+        joints.append(Joint("panda_hand_joint", F, (0, 0, 0), (0, 0, -0.785398163397)))
+    elif tip != "panda_link8":
+        raise ValueError(f"link not found: {tip}")
+    return RobotChain("panda", "panda_link0", tip, joints)
+
+
+PANDA_HOME = (0.0, -math.pi / 4, 0.0, -3.0 * math.pi / 4, 0.0, math.pi / 2, math.pi / 4)
+
+
+def ur5() -> RobotChain:
+    """UR5 (ur_description ur5.urdf.xacro, joint_limited=false), base_link -> ee_link."""
+    R, F = JOINT_REVOLUTE, JOINT_FIXED
+    P2 = math.pi / 2
+    tp = 2.0 * math.pi
+    joints = [
+        Joint("shoulder_pan_joint", R, (0, 0, 0.089159), (0, 0, 0), (0, 0, 1), -tp, tp, 3.15),
+        Joint("shoulder_lift_joint", R, (0, 0.13585, 0), (0, P2, 0), (0, 1, 0), -tp, tp, 3.15),
+        Joint("elbow_joint", R, (0, -0.1197, 0.425), (0, 0, 0), (0, 1, 0), -tp, tp, 3.15),
+        Joint("wrist_1_joint", R, (0, 0, 0.39225), (0, P2, 0), (0, 1, 0), -tp, tp, 3.2),
+        Joint("wrist_2_joint", R, (0, 0.093, 0), (0, 0, 0), (0, 0, 1), -tp, tp, 3.2),
+        Joint("wrist_3_joint", R, (0, 0, 0.09465), (0, 0, 0), (0, 1, 0), -tp, tp, 3.2),
+        Joint("ee_fixed_joint", F, (0, 0.0823, 0), (0, 0, P2)),
+    ]
+    return RobotChain("ur5", "base_link", "ee_link", joints)
+
+
+def fetch() -> RobotChain:
+    """Fetch, group arm_with_torso (fetch_description/robots/fetch.urdf), tip gripper_link."""
+    R, F, P = JOINT_REVOLUTE, JOINT_FIXED, JOINT_PRISMATIC
+    joints = [
+        Joint("torso_lift_joint", P, (-0.086875, 0, 0.37743), (-6.123e-17, 0, 0), (0, 0, 1), 0.0, 0.38615, 0.1),
+        Joint("shoulder_pan_joint", R, (0.119525, 0, 0.34858), (0, 0, 0), (0, 0, 1), -1.6056, 1.6056, 1.256),
+        Joint("shoulder_lift_joint", R, (0.117, 0, 0.06), (0, 0, 0), (0, 1, 0), -1.221, 1.518, 1.454),
+        Joint("upperarm_roll_joint", R, (0.219, 0, 0), (0, 0, 0), (1, 0, 0), velocity=1.571, continuous=True),
+        Joint("elbow_flex_joint", R, (0.133, 0, 0), (0, 0, 0), (0, 1, 0), -2.251, 2.251, 1.521),
+        Joint("forearm_roll_joint", R, (0.197, 0, 0), (0, 0, 0), (1, 0, 0), velocity=1.571, continuous=True),
+        Joint("wrist_flex_joint", R, (0.1245, 0, 0), (0, 0, 0), (0, 1, 0), -2.16, 2.16, 2.268),
+        Joint("wrist_roll_joint", R, (0.1385, 0, 0), (0, 0, 0), (1, 0, 0), velocity=2.268, continuous=True),
+        Joint("gripper_axis", F, (0.16645, 0, 0)),
+    ]
+    return RobotChain("fetch", "base_link", "gripper_link", joints)
+
+
+def rr(link1_length: float = 2.0) -> RobotChain:
+    """The in-code 2-R planar robot of the reference's tests
+    (/root/reference/tests/ik_tests.cpp:15-48 uses a->b at x=2; tests/robot_tests.cpp:9-38 x=1).
+    RobotModelBuilder::addChain gives revolute joints limits +-pi and no velocity limit."""
+    R, F = JOINT_REVOLUTE, JOINT_FIXED
+    joints = [
+        Joint("base-a-joint", R, (0, 0, 0), (0, 0, 0), (0, 0, 1), -math.pi, math.pi, 0.0),
+        Joint("a-b-joint", R, (link1_length, 0, 0), (0, 0, 0), (0, 0, 1), -math.pi, math.pi, 0.0),
+        Joint("b-ee-joint", F, (1.0, 0, 0)),
+    ]
+    return RobotChain("rr", "base", "ee", joints)
+
+
+def skew6() -> RobotChain:
+    """Synthetic 6-variable chain exercising general (non axis-aligned) revolute axes, a
+    general-axis prismatic joint, negative axes and interleaved fixed joints (no reference
+    counterpart; parity-test coverage for the REV_GENERAL / PRISMATIC device paths)."""
+    R, F, P = JOINT_REVOLUTE, JOINT_FIXED, JOINT_PRISMATIC
+    joints = [
+        Joint("f0", F, (0.1, 0.0, 0.2), (0.1, -0.2, 0.3)),
+        Joint("j0", R, (0, 0, 0.1), (0.3, 0, 0), (0, 0, -1), -2.5, 2.5, 2.0),
+        Joint("j1", R, (0.2, 0, 0), (0, 0.4, 0), (1, 1, 0), -2.0, 2.0, 1.5),
+        Joint("f1", F, (0.0, 0.05, 0.0), (0, 0, 0.5)),
+        Joint("j2", P, (0.1, 0, 0.1), (0, 0, 0), (1, 2, 2), -0.2, 0.3, 0.5),
+        Joint("j3", R, (0.25, 0, 0), (-0.7, 0.1, 0), (0, -1, 0), velocity=3.0, continuous=True),
+        Joint("j4", R, (0.15, 0.02, 0), (0, 0, 1.1), (1, 0, 0), -3.0, 3.0, 0.0),
+        Joint("j5", R, (0.1, 0, 0.05), (0.2, 0.2, 0.2), (0.3, -0.5, 0.8), -2.8, 2.8, 2.5),
+        Joint("f2", F, (0.05, 0, 0.08), (0, 1.0, 0)),
+        Joint("f3", F, (0.0, 0.01, 0.0), (0.5, 0, 0)),
+    ]
+    return RobotChain("skew6", "root", "tool", joints)
+
+
+ROBOTS = {"panda": panda, "ur5": ur5, "fetch": fetch, "rr": rr, "skew6": skew6}
