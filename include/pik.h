@@ -1,0 +1,180 @@
+/*
+ * pik.h -- C-ABI of the B200-native batched IK engine (libpik_b200.so).
+ *
+ * This is the drop-in boundary for pick_ik's memetic + numeric-gradient hot path.  Every entry
+ * point cites the reference interface it replaces (paths relative to pick_ik @ 8c99999).  Plain
+ * pointers and sizes only; no C++ / torch types; functions return 0 (PIK_OK) or a negative
+ * PIK_E_* status and never throw.  Handles are thread-compatible: one in-flight call per solver.
+ *
+ * Arithmetic: IEEE binary64 on the device (the reference computes in `double` everywhere).
+ * Wall-clock limits of the reference (max_time, memetic_gd_max_time, the plugin timeout) are
+ * replaced by the iteration caps of the same parameter set; see DESIGN.md.
+ */
+#ifndef PIK_H
+#define PIK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIK_MAX_VARS 16
+#define PIK_MAX_ELITES 32
+
+enum {
+    PIK_OK = 0,
+    PIK_E_INVALID_ARGUMENT = -1,
+    PIK_E_INVALID_ROBOT = -2,
+    PIK_E_INVALID_PARAMS = -3, /* a pick_ik_parameters.yaml validator failed */
+    PIK_E_CUDA = -4,
+    PIK_E_NO_DEVICE = -5,
+    PIK_E_OUT_OF_MEMORY = -6,
+    PIK_E_UNSUPPORTED = -7
+};
+
+/* moveit_msgs::msg::MoveItErrorCodes values written by pick_ik_plugin.cpp:212,215 */
+enum { PIK_SUCCESS = 1, PIK_NO_IK_SOLUTION = -31 };
+
+enum { PIK_JOINT_FIXED = 0, PIK_JOINT_REVOLUTE = 1, PIK_JOINT_PRISMATIC = 2 };
+enum { PIK_MODE_GLOBAL = 0, PIK_MODE_LOCAL = 1 }; /* yaml `mode`: "global" | "local" */
+enum { PIK_MEM_HOST = 0, PIK_MEM_DEVICE = 1 };
+
+/* One joint of the serial chain model-root -> tip link, in chain order.  Replaces what
+ * Robot::from (src/robot.cpp:44-85) and make_fk_fn (src/fk_moveit.cpp:11-35) read from the MoveIt
+ * RobotModel: joint type, LinkModel::getJointOriginTransform, joint axis, VariableBounds. */
+typedef struct pik_joint_desc {
+    int32_t type;        /* PIK_JOINT_* */
+    int32_t bounded;     /* VariableBounds::position_bounded_ (URDF continuous = 0) */
+    double origin_R[9];  /* parent link -> joint frame rotation, row-major */
+    double origin_t[3];
+    double axis[3];      /* unit axis (revolute / prismatic) */
+    double min_position; /* VariableBounds::min_position_ / max_position_ (continuous: -pi / pi) */
+    double max_position;
+    double max_velocity; /* VariableBounds::max_velocity_, 0 = none */
+} pik_joint_desc;
+
+/* Robot::Variable, include/pick_ik/robot.hpp:15-37 */
+typedef struct pik_variable {
+    double min, max, mid, half_span, max_velocity_rcp, minimal_displacement_factor;
+    int32_t bounded;
+    int32_t pad_;
+} pik_variable;
+
+/* src/pick_ik_parameters.yaml, same names and defaults; the YAML -> solver mapping of
+ * pick_ik_plugin.cpp:166-196 is applied inside the library. */
+typedef struct pik_params {
+    int32_t mode;
+    int32_t gd_max_iters;
+    double gd_step_size;
+    double gd_min_cost_delta;
+    double position_threshold;
+    double orientation_threshold;
+    double approximate_solution_position_threshold;    /* used by the plugin shim only */
+    double approximate_solution_orientation_threshold; /* used by the plugin shim only */
+    double approximate_solution_joint_threshold;       /* used by the plugin shim only */
+    double approximate_solution_cost_threshold;        /* used by the plugin shim only */
+    double cost_threshold;
+    double position_scale;
+    double rotation_scale;
+    double center_joints_weight;
+    double avoid_joint_limits_weight;
+    double minimal_displacement_weight;
+    double memetic_wipeout_fitness_tol;
+    double memetic_gd_max_time; /* accepted, ignored: replaced by memetic_gd_max_iters */
+    int32_t stop_optimization_on_valid_solution;
+    int32_t memetic_num_threads;            /* species; the batch API runs one (ik_memetic.cpp:299) */
+    int32_t memetic_stop_on_first_solution;
+    int32_t memetic_population_size;
+    int32_t memetic_elite_size;
+    int32_t memetic_max_generations;
+    int32_t memetic_gd_max_iters;
+    int32_t return_approximate_solution; /* KinematicsQueryOptions::return_approximate_solution */
+    uint64_t rng_seed; /* the reference RNG is unseeded; ours is Philox4x32-10 keyed by this */
+} pik_params;
+
+/* counters of the last pik_solve_batch on a solver */
+typedef struct pik_stats {
+    int64_t problems;
+    int64_t solved;
+    int64_t generation_launches;  /* memetic generation kernel launches */
+    int64_t kernel_launches;      /* all kernels launched by the call */
+    int64_t problem_generations;  /* sum over problems of generations executed */
+    int64_t gd_steps;             /* GD step() executions */
+    double device_ms;             /* CUDA-event time of the call's device work */
+} pik_stats;
+
+typedef struct pik_robot pik_robot;
+typedef struct pik_solver pik_solver;
+
+int pik_version(void);
+const char* pik_status_string(int status);
+
+/* defaults of src/pick_ik_parameters.yaml */
+void pik_params_default(pik_params* p);
+/* the YAML validators (one_of / gt_eq) plus elite <= population and table limits */
+int pik_params_validate(const pik_params* p);
+
+/* Robot::from + chain flattening (src/robot.cpp:44-85; src/pick_ik_plugin.cpp:65-68) */
+int pik_robot_create(const pik_joint_desc* joints, int32_t n_joints, pik_robot** out);
+void pik_robot_destroy(pik_robot* robot);
+int32_t pik_robot_num_variables(const pik_robot* robot);
+int pik_robot_get_variable(const pik_robot* robot, int32_t i, pik_variable* out);
+/* Robot::is_valid_configuration, src/robot.cpp:97-105 (host) */
+int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q);
+
+/* stream: a cudaStream_t (or NULL for a stream owned by the solver) */
+int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_solver** out);
+void pik_solver_destroy(pik_solver* solver);
+
+/*
+ * Batched replacement for the solve in PickIKPlugin::searchPositionIK
+ * (src/pick_ik_plugin.cpp:162-217): ik_memetic (src/ik_memetic.cpp:285-373, one species) when
+ * mode == global, ik_gradient (src/ik_gradient.cpp:96-139) when mode == local, for B independent
+ * problems.
+ *   goal_pose  [B][7]  px py pz qw qx qy qz of the tip in the model frame (the goal_frames of
+ *                      pick_ik_plugin.cpp:88-94; quaternion used un-normalised like tf2::fromMsg)
+ *   seed       [B][n] (seed_stride = n) or [n] (seed_stride = 0): ik_seed_state
+ *   solution   [B][n]  genes on success, the seed on failure (pick_ik_plugin.cpp:213,216)
+ *   error_code [B]     PIK_SUCCESS / PIK_NO_IK_SOLUTION
+ *   cost       [B]     best cost found (may be NULL)
+ *   iterations [B]     generations (global) / GD iterations (local) executed (may be NULL)
+ * first_problem_index offsets the RNG stream key so a shard of a larger batch reproduces the
+ * unsharded result.  memory: PIK_MEM_HOST (host pointers; the copies to and from the device are
+ * part of the call) or PIK_MEM_DEVICE (device pointers on the solver's device).  The call returns
+ * when the results are complete.
+ */
+int pik_solve_batch(pik_solver* solver, const pik_params* params, int64_t B,
+                    int64_t first_problem_index, const double* goal_pose, const double* seed,
+                    int64_t seed_stride, double* solution, int32_t* error_code, double* cost,
+                    int32_t* iterations, int32_t memory);
+
+/*
+ * Batched FK + cost + solution test: make_cost_fn (src/goal.cpp:188-203),
+ * make_is_solution_test_fn (src/goal.cpp:163-186) and the tip frame of make_fk_fn
+ * (src/fk_moveit.cpp:20-34) for B configurations q [B][n].  Outputs may be NULL.
+ * tip_pose [B][7] = px py pz qw qx qy qz.
+ */
+int pik_eval_cost(pik_solver* solver, const pik_params* params, int64_t B, const double* goal_pose,
+                  const double* seed, int64_t seed_stride, const double* q, double* cost,
+                  int32_t* is_solution, double* tip_pose, int32_t memory);
+
+int pik_solver_synchronize(pik_solver* solver);
+
+/* number of CUDA devices visible (0 if none) */
+int pik_device_count(void);
+/* page-locked host buffers for PIK_MEM_HOST calls (optional; any host memory is accepted) */
+int pik_host_alloc(void** out, size_t bytes);
+void pik_host_free(void* p);
+/* FP64 FMA throughput of the solver's device in TFLOP/s, measured with independent DFMA chains on
+ * every SM; bench.py reports the FP64 roofline fraction against it. */
+int pik_measure_fp64_peak(pik_solver* solver, double* tflops);
+int pik_solver_get_stats(pik_solver* solver, pik_stats* out);
+/* last CUDA error text of this solver (empty string if none) */
+const char* pik_solver_last_error(const pik_solver* solver);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,267 @@
+"""ctypes binding of the C-ABI in include/pik.h (libpik_b200.so).
+
+This is the only compute path of the package: there is no CPU fallback.  Importing works without a
+GPU (so the symbol table can be checked); creating a ``Solver`` without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .robots import JOINT_DESC_DTYPE, RobotChain
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpik_b200.so")
+
+PIK_OK = 0
+PIK_SUCCESS = 1
+PIK_NO_IK_SOLUTION = -31
+MODE_GLOBAL, MODE_LOCAL = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+
+# every symbol include/pik.h declares
+EXPORTS = [
+    "pik_version", "pik_status_string", "pik_params_default", "pik_params_validate", "pik_robot_create",
+    "pik_robot_destroy", "pik_robot_num_variables", "pik_robot_get_variable",
+    "pik_robot_is_valid_configuration", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
+    "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
+    "pik_device_count", "pik_host_alloc", "pik_host_free", "pik_measure_fp64_peak",
+]
+
+
+class PikError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        msg = f"{where}: {status_string(status)} ({status})"
+        if detail:
+            msg += f": {detail}"
+        super().__init__(msg)
+
+
+class Params(C.Structure):
+    """pik_params: src/pick_ik_parameters.yaml names and defaults (+ rng_seed)."""
+
+    _fields_ = [
+        ("mode", C.c_int32), ("gd_max_iters", C.c_int32), ("gd_step_size", C.c_double),
+        ("gd_min_cost_delta", C.c_double), ("position_threshold", C.c_double),
+        ("orientation_threshold", C.c_double), ("approximate_solution_position_threshold", C.c_double),
+        ("approximate_solution_orientation_threshold", C.c_double),
+        ("approximate_solution_joint_threshold", C.c_double),
+        ("approximate_solution_cost_threshold", C.c_double), ("cost_threshold", C.c_double),
+        ("position_scale", C.c_double), ("rotation_scale", C.c_double), ("center_joints_weight", C.c_double),
+        ("avoid_joint_limits_weight", C.c_double), ("minimal_displacement_weight", C.c_double),
+        ("memetic_wipeout_fitness_tol", C.c_double), ("memetic_gd_max_time", C.c_double),
+        ("stop_optimization_on_valid_solution", C.c_int32), ("memetic_num_threads", C.c_int32),
+        ("memetic_stop_on_first_solution", C.c_int32), ("memetic_population_size", C.c_int32),
+        ("memetic_elite_size", C.c_int32), ("memetic_max_generations", C.c_int32),
+        ("memetic_gd_max_iters", C.c_int32), ("return_approximate_solution", C.c_int32),
+        ("rng_seed", C.c_uint64),
+    ]
+
+
+class Variable(C.Structure):
+    _fields_ = [("min", C.c_double), ("max", C.c_double), ("mid", C.c_double), ("half_span", C.c_double),
+                ("max_velocity_rcp", C.c_double), ("minimal_displacement_factor", C.c_double),
+                ("bounded", C.c_int32), ("pad_", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("problems", C.c_int64), ("solved", C.c_int64), ("generation_launches", C.c_int64),
+                ("kernel_launches", C.c_int64), ("problem_generations", C.c_int64), ("gd_steps", C.c_int64),
+                ("device_ms", C.c_double)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Loads libpik_b200.so; raises if it has not been built (python -m pick_ik_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m pick_ik_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.c_void_p, C.c_void_p  # raw addresses: host or device
+    L.pik_version.restype = C.c_int
+    L.pik_status_string.restype = C.c_char_p
+    L.pik_status_string.argtypes = [C.c_int]
+    L.pik_params_default.restype = None
+    L.pik_params_default.argtypes = [C.POINTER(Params)]
+    L.pik_params_validate.argtypes = [C.POINTER(Params)]
+    L.pik_robot_create.argtypes = [vp, C.c_int32, C.POINTER(vp)]
+    L.pik_robot_destroy.restype = None
+    L.pik_robot_destroy.argtypes = [vp]
+    L.pik_robot_num_variables.restype = C.c_int32
+    L.pik_robot_num_variables.argtypes = [vp]
+    L.pik_robot_get_variable.argtypes = [vp, C.c_int32, C.POINTER(Variable)]
+    L.pik_robot_is_valid_configuration.argtypes = [vp, dp]
+    L.pik_solver_create.argtypes = [vp, C.c_int32, vp, C.POINTER(vp)]
+    L.pik_solver_destroy.restype = None
+    L.pik_solver_destroy.argtypes = [vp]
+    L.pik_solve_batch.argtypes = [vp, C.POINTER(Params), C.c_int64, C.c_int64, dp, dp, C.c_int64, dp, ip, dp, ip,
+                                  C.c_int32]
+    L.pik_eval_cost.argtypes = [vp, C.POINTER(Params), C.c_int64, dp, dp, C.c_int64, dp, dp, ip, dp, C.c_int32]
+    L.pik_solver_synchronize.argtypes = [vp]
+    L.pik_solver_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.pik_solver_last_error.restype = C.c_char_p
+    L.pik_solver_last_error.argtypes = [vp]
+    L.pik_device_count.restype = C.c_int
+    L.pik_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.pik_host_free.restype = None
+    L.pik_host_free.argtypes = [vp]
+    L.pik_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def status_string(status: int) -> str:
+    return lib().pik_status_string(int(status)).decode()
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().pik_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k == "mode" and isinstance(v, str):
+            if v not in ("global", "local"):
+                raise ValueError("mode must be one of ['global', 'local']")
+            v = {"global": MODE_GLOBAL, "local": MODE_LOCAL}[v]
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def validate_params(p: Params) -> int:
+    return lib().pik_params_validate(C.byref(p))
+
+
+def device_count() -> int:
+    return lib().pik_device_count()
+
+
+class Robot:
+    """pik_robot: the flattened chain + Robot::Variable table (src/robot.cpp:44-85)."""
+
+    def __init__(self, chain_or_desc):
+        desc = chain_or_desc.joint_desc() if isinstance(chain_or_desc, RobotChain) else chain_or_desc
+        desc = np.ascontiguousarray(desc, dtype=JOINT_DESC_DTYPE)
+        self.desc = desc
+        h = C.c_void_p()
+        rc = lib().pik_robot_create(desc.ctypes.data_as(C.c_void_p), len(desc), C.byref(h))
+        if rc != PIK_OK:
+            raise PikError(rc, "pik_robot_create")
+        self.handle = h
+        self.n = lib().pik_robot_num_variables(h)
+
+    def variable(self, i: int) -> Variable:
+        v = Variable()
+        rc = lib().pik_robot_get_variable(self.handle, i, C.byref(v))
+        if rc != PIK_OK:
+            raise PikError(rc, "pik_robot_get_variable")
+        return v
+
+    def is_valid_configuration(self, q) -> bool:
+        qa = np.ascontiguousarray(q, dtype=np.float64)
+        assert qa.shape == (self.n,)
+        return bool(lib().pik_robot_is_valid_configuration(self.handle, qa.ctypes.data_as(C.c_void_p)))
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.pik_robot_destroy(h)
+
+
+def _addr(a) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+class Solver:
+    """pik_solver on one CUDA device."""
+
+    def __init__(self, robot: Robot, device: int = 0, stream: int = 0):
+        self.robot = robot
+        self.n = robot.n
+        h = C.c_void_p()
+        rc = lib().pik_solver_create(robot.handle, device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != PIK_OK:
+            raise PikError(rc, "pik_solver_create")
+        self.handle = h
+
+    def _check(self, rc: int, where: str):
+        if rc != PIK_OK:
+            raise PikError(rc, where, lib().pik_solver_last_error(self.handle).decode())
+
+    # -- host-memory API (numpy) --------------------------------------------------------------
+    def solve_batch(self, params: Params, goal_pose: np.ndarray, seed: np.ndarray, first_problem_index: int = 0,
+                    out: Optional[dict] = None) -> dict:
+        goal_pose = np.ascontiguousarray(goal_pose, dtype=np.float64)
+        if goal_pose.ndim != 2 or goal_pose.shape[1] != 7:
+            raise ValueError("goal_pose must be [B, 7]")
+        B = goal_pose.shape[0]
+        seed = np.ascontiguousarray(seed, dtype=np.float64)
+        if seed.shape == (self.n,) or seed.shape == (1, self.n):
+            stride = 0
+        elif seed.shape == (B, self.n):
+            stride = self.n
+        else:
+            raise ValueError("seed must be [n] or [B, n]")
+        if out is None:
+            out = dict(solution=np.empty((B, self.n)), error_code=np.empty(B, dtype=np.int32), cost=np.empty(B),
+                       iterations=np.empty(B, dtype=np.int32))
+        rc = lib().pik_solve_batch(self.handle, C.byref(params), B, first_problem_index, _addr(goal_pose),
+                                   _addr(seed), stride, _addr(out["solution"]), _addr(out["error_code"]),
+                                   _addr(out["cost"]), _addr(out["iterations"]), MEM_HOST)
+        self._check(rc, "pik_solve_batch")
+        return out
+
+    def eval_cost(self, params: Params, goal_pose: np.ndarray, seed: np.ndarray, q: np.ndarray):
+        goal_pose = np.ascontiguousarray(goal_pose, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        B = q.shape[0]
+        assert q.shape == (B, self.n) and goal_pose.shape == (B, 7)
+        seed = np.ascontiguousarray(seed, dtype=np.float64)
+        stride = 0 if seed.shape in ((self.n,), (1, self.n)) else self.n
+        cost = np.empty(B)
+        sol = np.empty(B, dtype=np.int32)
+        tip = np.empty((B, 7))
+        rc = lib().pik_eval_cost(self.handle, C.byref(params), B, _addr(goal_pose), _addr(seed), stride, _addr(q),
+                                 _addr(cost), _addr(sol), _addr(tip), MEM_HOST)
+        self._check(rc, "pik_eval_cost")
+        return cost, sol, tip
+
+    # -- raw-pointer API (device or pinned host addresses) ---------------------------------------
+    def solve_batch_ptr(self, params: Params, B: int, first_problem_index: int, goal_pose: int, seed: int,
+                        seed_stride: int, solution: int, error_code: int, cost: int, iterations: int,
+                        memory: int = MEM_DEVICE):
+        rc = lib().pik_solve_batch(self.handle, C.byref(params), B, first_problem_index, goal_pose, seed, seed_stride,
+                                   solution, error_code, cost or None, iterations or None, memory)
+        self._check(rc, "pik_solve_batch")
+
+    def synchronize(self):
+        self._check(lib().pik_solver_synchronize(self.handle), "pik_solver_synchronize")
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(lib().pik_solver_get_stats(self.handle, C.byref(s)), "pik_solver_get_stats")
+        return s
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        self._check(lib().pik_measure_fp64_peak(self.handle, C.byref(v)), "pik_measure_fp64_peak")
+        return v.value
+
+    def close(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.pik_solver_destroy(h)
+
+    def __del__(self):
+        self.close()

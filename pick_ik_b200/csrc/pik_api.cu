@@ -1,0 +1,468 @@
+// pik_api.cu -- the C-ABI of include/pik.h: robot tables, solver handles, device buffers, launches.
+// No CPU solve path exists here: every entry point that computes runs the CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/pik.h"
+#include "pik_host_robot.h"
+#include "pik_kernels.cuh"
+
+using namespace pik;
+
+struct pik_robot {
+    DevRobot dev;
+    pik_variable vars[kMaxVars];
+};
+
+namespace {
+
+struct DeviceArray {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct pik_solver {
+    pik_robot robot;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int32_t* h_counters = nullptr;            // pinned [2]
+    unsigned long long* h_stats = nullptr;    // pinned [4]
+    // staging for PIK_MEM_HOST calls
+    DeviceArray d_goal, d_seed, d_q, d_solution, d_error, d_cost, d_iters, d_issol, d_tip;
+    // solver state
+    DeviceArray d_pop, d_order, d_hdr, d_meta, d_active, d_counters, d_stats;
+    pik_stats stats{};
+    std::string last_error;
+};
+
+namespace {
+
+int fail_cuda(pik_solver* s, cudaError_t e, const char* what) {
+    if (s) s->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? PIK_E_OUT_OF_MEMORY : PIK_E_CUDA;
+}
+
+#define PIK_CUDA(s, call)                                         \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return fail_cuda((s), e__, #call); \
+    } while (0)
+
+int ensure(pik_solver* s, DeviceArray& a, size_t bytes) {
+    if (bytes <= a.bytes) return PIK_OK;
+    if (a.ptr) {
+        PIK_CUDA(s, cudaStreamSynchronize(s->stream));
+        PIK_CUDA(s, cudaFree(a.ptr));
+        a.ptr = nullptr;
+        a.bytes = 0;
+    }
+    PIK_CUDA(s, cudaMalloc(&a.ptr, bytes));
+    a.bytes = bytes;
+    return PIK_OK;
+}
+
+void release(DeviceArray& a) {
+    if (a.ptr) cudaFree(a.ptr);
+    a.ptr = nullptr;
+    a.bytes = 0;
+}
+
+bool finite_ge(double v, double lo) { return v == v && v >= lo; }
+
+}  // namespace
+
+extern "C" {
+
+int pik_version(void) { return 100; }
+
+const char* pik_status_string(int status) {
+    switch (status) {
+        case PIK_OK: return "ok";
+        case PIK_E_INVALID_ARGUMENT: return "invalid argument";
+        case PIK_E_INVALID_ROBOT: return "invalid robot description";
+        case PIK_E_INVALID_PARAMS: return "parameter validation failed";
+        case PIK_E_CUDA: return "CUDA error";
+        case PIK_E_NO_DEVICE: return "no CUDA device";
+        case PIK_E_OUT_OF_MEMORY: return "out of device memory";
+        case PIK_E_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+void pik_params_default(pik_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->mode = PIK_MODE_GLOBAL;
+    p->gd_step_size = 0.0001;
+    p->gd_max_iters = 100;
+    p->gd_min_cost_delta = 1.0e-12;
+    p->position_threshold = 0.001;
+    p->orientation_threshold = 0.001;
+    p->approximate_solution_position_threshold = 0.05;
+    p->approximate_solution_orientation_threshold = 0.05;
+    p->approximate_solution_joint_threshold = 0.0;
+    p->approximate_solution_cost_threshold = 0.0;
+    p->cost_threshold = 0.001;
+    p->position_scale = 1.0;
+    p->rotation_scale = 0.5;
+    p->center_joints_weight = 0.0;
+    p->avoid_joint_limits_weight = 0.0;
+    p->minimal_displacement_weight = 0.0;
+    p->stop_optimization_on_valid_solution = 1;
+    p->memetic_num_threads = 1;
+    p->memetic_stop_on_first_solution = 1;
+    p->memetic_population_size = 16;
+    p->memetic_elite_size = 4;
+    p->memetic_wipeout_fitness_tol = 0.00001;
+    p->memetic_max_generations = 100;
+    p->memetic_gd_max_iters = 25;
+    p->memetic_gd_max_time = 0.005;
+    p->return_approximate_solution = 0;
+    p->rng_seed = 0x5EED;
+}
+
+int pik_params_validate(const pik_params* p) {
+    if (!p) return PIK_E_INVALID_ARGUMENT;
+    // src/pick_ik_parameters.yaml validators
+    if (p->mode != PIK_MODE_GLOBAL && p->mode != PIK_MODE_LOCAL) return PIK_E_INVALID_PARAMS;
+    if (!finite_ge(p->gd_step_size, 1.0e-12)) return PIK_E_INVALID_PARAMS;
+    if (p->gd_max_iters < 1) return PIK_E_INVALID_PARAMS;
+    if (!finite_ge(p->gd_min_cost_delta, 1.0e-64)) return PIK_E_INVALID_PARAMS;
+    const double ge0[] = {p->position_threshold, p->orientation_threshold,
+                          p->approximate_solution_position_threshold, p->approximate_solution_orientation_threshold,
+                          p->approximate_solution_joint_threshold, p->approximate_solution_cost_threshold,
+                          p->cost_threshold, p->position_scale, p->rotation_scale, p->center_joints_weight,
+                          p->avoid_joint_limits_weight, p->minimal_displacement_weight,
+                          p->memetic_wipeout_fitness_tol, p->memetic_gd_max_time};
+    for (double v : ge0)
+        if (!finite_ge(v, 0.0)) return PIK_E_INVALID_PARAMS;
+    if (p->memetic_num_threads < 1 || p->memetic_population_size < 1 || p->memetic_elite_size < 1 ||
+        p->memetic_max_generations < 1 || p->memetic_gd_max_iters < 1)
+        return PIK_E_INVALID_PARAMS;
+    // beyond the YAML: the reference leaves elite > population unguarded; table limits
+    if (p->memetic_elite_size > p->memetic_population_size) return PIK_E_INVALID_PARAMS;
+    if (p->memetic_elite_size > kMaxElites || p->memetic_population_size > kMaxPopulation) return PIK_E_UNSUPPORTED;
+    return PIK_OK;
+}
+
+int pik_robot_create(const pik_joint_desc* joints, int32_t n_joints, pik_robot** out) {
+    if (!out) return PIK_E_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!joints || n_joints <= 0) return PIK_E_INVALID_ROBOT;
+    for (int j = 0; j < n_joints; ++j) {
+        const pik_joint_desc& jd = joints[j];
+        if (jd.type == PIK_JOINT_FIXED) continue;
+        if (jd.type != PIK_JOINT_REVOLUTE && jd.type != PIK_JOINT_PRISMATIC) return PIK_E_INVALID_ROBOT;
+        const double a2 = jd.axis[0] * jd.axis[0] + jd.axis[1] * jd.axis[1] + jd.axis[2] * jd.axis[2];
+        if (!(std::fabs(a2 - 1.0) < 1e-6)) return PIK_E_INVALID_ROBOT;
+        if (!(jd.min_position <= jd.max_position)) return PIK_E_INVALID_ROBOT;
+    }
+    pik_robot* r = new (std::nothrow) pik_robot;
+    if (!r) return PIK_E_OUT_OF_MEMORY;
+    const int rc = build_dev_robot(joints, n_joints, &r->dev);
+    if (rc != PIK_OK) {
+        delete r;
+        return rc;
+    }
+    double rcp[kMaxVars] = {0};
+    host_max_velocity_rcp(joints, n_joints, rcp);
+    for (int i = 0; i < r->dev.n; ++i) {
+        pik_variable& v = r->vars[i];
+        v.min = r->dev.vmin[i];
+        v.max = r->dev.vmax[i];
+        v.mid = r->dev.vmid[i];
+        v.half_span = r->dev.vhalf[i];
+        v.max_velocity_rcp = rcp[i];
+        v.minimal_displacement_factor = r->dev.vfac[i];
+        v.bounded = r->dev.bounded[i];
+        v.pad_ = 0;
+    }
+    *out = r;
+    return PIK_OK;
+}
+
+void pik_robot_destroy(pik_robot* robot) { delete robot; }
+
+int32_t pik_robot_num_variables(const pik_robot* robot) { return robot ? robot->dev.n : 0; }
+
+int pik_robot_get_variable(const pik_robot* robot, int32_t i, pik_variable* out) {
+    if (!robot || !out || i < 0 || i >= robot->dev.n) return PIK_E_INVALID_ARGUMENT;
+    *out = robot->vars[i];
+    return PIK_OK;
+}
+
+int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q) {
+    if (!robot || !q) return 0;
+    for (int i = 0; i < robot->dev.n; ++i) {
+        const pik_variable& v = robot->vars[i];
+        if (!(!v.bounded || (q[i] <= v.max && q[i] >= v.min))) return 0;  // robot.cpp:32-34
+    }
+    return 1;
+}
+
+int pik_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_solver** out) {
+    if (!out) return PIK_E_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!robot) return PIK_E_INVALID_ARGUMENT;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return PIK_E_NO_DEVICE;
+    if (device < 0 || device >= count) return PIK_E_INVALID_ARGUMENT;
+    pik_solver* s = new (std::nothrow) pik_solver;
+    if (!s) return PIK_E_OUT_OF_MEMORY;
+    s->robot = *robot;
+    s->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        if (stream) {
+            s->stream = static_cast<cudaStream_t>(stream);
+        } else {
+            e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+            s->own_stream = true;
+        }
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_counters), 2 * sizeof(int32_t), cudaHostAllocDefault);
+    if (e == cudaSuccess)
+        e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_stats), 4 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = configure_kernels();
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "pik_solver_create: %s\n", cudaGetErrorString(e));
+        pik_solver_destroy(s);
+        return PIK_E_CUDA;
+    }
+    *out = s;
+    return PIK_OK;
+}
+
+void pik_solver_destroy(pik_solver* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    DeviceArray* arrays[] = {&s->d_goal, &s->d_seed, &s->d_q, &s->d_solution, &s->d_error, &s->d_cost, &s->d_iters,
+                             &s->d_issol, &s->d_tip, &s->d_pop, &s->d_order, &s->d_hdr, &s->d_meta, &s->d_active,
+                             &s->d_counters, &s->d_stats};
+    for (DeviceArray* a : arrays) release(*a);
+    if (s->h_counters) cudaFreeHost(s->h_counters);
+    if (s->h_stats) cudaFreeHost(s->h_stats);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
+                    const double* goal_pose, const double* seed, int64_t seed_stride, double* solution,
+                    int32_t* error_code, double* cost, int32_t* iterations, int32_t memory) {
+    if (!s) return PIK_E_INVALID_ARGUMENT;
+    s->last_error.clear();
+    if (!params || B < 0 || !goal_pose || !seed || !solution || !error_code) return PIK_E_INVALID_ARGUMENT;
+    const int n = s->robot.dev.n;
+    if (seed_stride != 0 && seed_stride != n) return PIK_E_INVALID_ARGUMENT;
+    if (memory != PIK_MEM_HOST && memory != PIK_MEM_DEVICE) return PIK_E_INVALID_ARGUMENT;
+    if (B > (int64_t)1 << 30 || first_problem_index < 0 || first_problem_index + B > (int64_t)0xffffffffll)
+        return PIK_E_INVALID_ARGUMENT;
+    int rc = pik_params_validate(params);
+    if (rc != PIK_OK) return rc;
+    std::memset(&s->stats, 0, sizeof(s->stats));
+    s->stats.problems = B;
+    if (B == 0) return PIK_OK;
+    PIK_CUDA(s, cudaSetDevice(s->device));
+    const DevParams pr = make_dev_params(*params);
+    const int P = pr.P;
+    const size_t seed_elems = seed_stride ? (size_t)B * n : (size_t)n;
+
+    SolveBuffers sb;
+    std::memset(&sb, 0, sizeof(sb));
+    sb.B = B;
+    sb.first_problem_index = first_problem_index;
+    sb.seed_stride = seed_stride;
+    if (memory == PIK_MEM_HOST) {
+        if ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8)) ||
+            (rc = ensure(s, s->d_solution, (size_t)B * n * 8)) || (rc = ensure(s, s->d_error, (size_t)B * 4)) ||
+            (rc = ensure(s, s->d_cost, (size_t)B * 8)) || (rc = ensure(s, s->d_iters, (size_t)B * 4)))
+            return rc;
+        sb.goal_pose = static_cast<double*>(s->d_goal.ptr);
+        sb.seed = static_cast<double*>(s->d_seed.ptr);
+        sb.solution = static_cast<double*>(s->d_solution.ptr);
+        sb.error_code = static_cast<int32_t*>(s->d_error.ptr);
+        sb.cost = static_cast<double*>(s->d_cost.ptr);
+        sb.iterations = static_cast<int32_t*>(s->d_iters.ptr);
+    } else {
+        sb.goal_pose = goal_pose;
+        sb.seed = seed;
+        sb.solution = solution;
+        sb.error_code = error_code;
+        sb.cost = cost;
+        sb.iterations = iterations;
+    }
+    if ((rc = ensure(s, s->d_stats, 4 * sizeof(unsigned long long)))) return rc;
+    sb.stats = static_cast<unsigned long long*>(s->d_stats.ptr);
+    const bool global = params->mode == PIK_MODE_GLOBAL;
+    if (global) {
+        const size_t F = 2 * (size_t)n + 2;
+        if ((rc = ensure(s, s->d_pop, 2 * (size_t)B * F * P * 8)) || (rc = ensure(s, s->d_order, (size_t)B * P * 2)) ||
+            (rc = ensure(s, s->d_hdr, (size_t)B * (n + 2) * 8)) || (rc = ensure(s, s->d_meta, (size_t)B * sizeof(ProblemMeta))) ||
+            (rc = ensure(s, s->d_active, 2 * (size_t)B * 4)) || (rc = ensure(s, s->d_counters, 2 * 4)))
+            return rc;
+        sb.pop = static_cast<double*>(s->d_pop.ptr);
+        sb.order = static_cast<uint16_t*>(s->d_order.ptr);
+        sb.hdr = static_cast<double*>(s->d_hdr.ptr);
+        sb.meta = static_cast<ProblemMeta*>(s->d_meta.ptr);
+        sb.active = static_cast<int32_t*>(s->d_active.ptr);
+        sb.counters = static_cast<int32_t*>(s->d_counters.ptr);
+    }
+
+    cudaStream_t st = s->stream;
+    PIK_CUDA(s, cudaEventRecord(s->ev0, st));
+    if (memory == PIK_MEM_HOST) {
+        PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
+        PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
+    }
+    PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 4 * sizeof(unsigned long long), st));
+    if (!global) {
+        PIK_CUDA(s, launch_gd_local(st, s->robot.dev, pr, sb));
+        s->stats.kernel_launches += 1;
+    } else {
+        PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, 2 * sizeof(int32_t), st));
+        PIK_CUDA(s, launch_memetic_init(st, s->robot.dev, pr, sb));
+        s->stats.kernel_launches += 1;
+        PIK_CUDA(s, cudaMemcpyAsync(s->h_counters, sb.counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PIK_CUDA(s, cudaStreamSynchronize(st));
+        int64_t n_active = s->h_counters[0];
+        int list = 0;
+        for (int gen = 0; gen < pr.max_generations && n_active > 0; ++gen) {
+            PIK_CUDA(s, cudaMemsetAsync(sb.counters + (list ^ 1), 0, sizeof(int32_t), st));
+            PIK_CUDA(s, launch_memetic_generation(st, s->robot.dev, pr, sb, list, n_active));
+            s->stats.kernel_launches += 1;
+            s->stats.generation_launches += 1;
+            PIK_CUDA(s, cudaMemcpyAsync(s->h_counters + (list ^ 1), sb.counters + (list ^ 1), sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, st));
+            PIK_CUDA(s, cudaStreamSynchronize(st));
+            n_active = s->h_counters[list ^ 1];
+            list ^= 1;
+        }
+    }
+    if (memory == PIK_MEM_HOST) {
+        PIK_CUDA(s, cudaMemcpyAsync(solution, sb.solution, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));
+        PIK_CUDA(s, cudaMemcpyAsync(error_code, sb.error_code, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, sb.cost, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+        if (iterations) PIK_CUDA(s, cudaMemcpyAsync(iterations, sb.iterations, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    }
+    PIK_CUDA(s, cudaMemcpyAsync(s->h_stats, sb.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    PIK_CUDA(s, cudaEventRecord(s->ev1, st));
+    PIK_CUDA(s, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    PIK_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->stats.device_ms = ms;
+    s->stats.problem_generations = (int64_t)s->h_stats[0];
+    s->stats.gd_steps = (int64_t)s->h_stats[1];
+    s->stats.solved = (int64_t)s->h_stats[2];
+    return PIK_OK;
+}
+
+int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const double* goal_pose, const double* seed,
+                  int64_t seed_stride, const double* q, double* cost, int32_t* is_solution, double* tip_pose,
+                  int32_t memory) {
+    if (!s) return PIK_E_INVALID_ARGUMENT;
+    s->last_error.clear();
+    if (!params || B < 0 || !goal_pose || !seed || !q) return PIK_E_INVALID_ARGUMENT;
+    const int n = s->robot.dev.n;
+    if (seed_stride != 0 && seed_stride != n) return PIK_E_INVALID_ARGUMENT;
+    if (memory != PIK_MEM_HOST && memory != PIK_MEM_DEVICE) return PIK_E_INVALID_ARGUMENT;
+    int rc = pik_params_validate(params);
+    if (rc != PIK_OK) return rc;
+    if (B == 0) return PIK_OK;
+    PIK_CUDA(s, cudaSetDevice(s->device));
+    const DevParams pr = make_dev_params(*params);
+    cudaStream_t st = s->stream;
+    if (memory == PIK_MEM_DEVICE) {
+        PIK_CUDA(s, launch_eval_cost(st, s->robot.dev, pr, B, goal_pose, seed, seed_stride, q, cost, is_solution, tip_pose));
+        return PIK_OK;
+    }
+    const size_t seed_elems = seed_stride ? (size_t)B * n : (size_t)n;
+    if ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8)) ||
+        (rc = ensure(s, s->d_q, (size_t)B * n * 8)) || (rc = ensure(s, s->d_cost, (size_t)B * 8)) ||
+        (rc = ensure(s, s->d_issol, (size_t)B * 4)) || (rc = ensure(s, s->d_tip, (size_t)B * 7 * 8)))
+        return rc;
+    PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
+    PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
+    PIK_CUDA(s, cudaMemcpyAsync(s->d_q.ptr, q, (size_t)B * n * 8, cudaMemcpyHostToDevice, st));
+    PIK_CUDA(s, launch_eval_cost(st, s->robot.dev, pr, B, static_cast<double*>(s->d_goal.ptr),
+                                 static_cast<double*>(s->d_seed.ptr), seed_stride, static_cast<double*>(s->d_q.ptr),
+                                 cost ? static_cast<double*>(s->d_cost.ptr) : nullptr,
+                                 is_solution ? static_cast<int32_t*>(s->d_issol.ptr) : nullptr,
+                                 tip_pose ? static_cast<double*>(s->d_tip.ptr) : nullptr));
+    if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, s->d_cost.ptr, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (is_solution) PIK_CUDA(s, cudaMemcpyAsync(is_solution, s->d_issol.ptr, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (tip_pose) PIK_CUDA(s, cudaMemcpyAsync(tip_pose, s->d_tip.ptr, (size_t)B * 7 * 8, cudaMemcpyDeviceToHost, st));
+    PIK_CUDA(s, cudaStreamSynchronize(st));
+    return PIK_OK;
+}
+
+int pik_solver_synchronize(pik_solver* s) {
+    if (!s) return PIK_E_INVALID_ARGUMENT;
+    PIK_CUDA(s, cudaSetDevice(s->device));
+    PIK_CUDA(s, cudaStreamSynchronize(s->stream));
+    return PIK_OK;
+}
+
+int pik_solver_get_stats(pik_solver* s, pik_stats* out) {
+    if (!s || !out) return PIK_E_INVALID_ARGUMENT;
+    *out = s->stats;
+    return PIK_OK;
+}
+
+const char* pik_solver_last_error(const pik_solver* s) { return s ? s->last_error.c_str() : ""; }
+
+int pik_host_alloc(void** out, size_t bytes) {
+    if (!out) return PIK_E_INVALID_ARGUMENT;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    return e == cudaSuccess ? PIK_OK : (e == cudaErrorMemoryAllocation ? PIK_E_OUT_OF_MEMORY : PIK_E_CUDA);
+}
+
+void pik_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int pik_measure_fp64_peak(pik_solver* s, double* tflops) {
+    if (!s || !tflops) return PIK_E_INVALID_ARGUMENT;
+    PIK_CUDA(s, cudaSetDevice(s->device));
+    cudaDeviceProp prop;
+    PIK_CUDA(s, cudaGetDeviceProperties(&prop, s->device));
+    int rc = ensure(s, s->d_stats, 4 * sizeof(unsigned long long));
+    if (rc) return rc;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        PIK_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+        PIK_CUDA(s, launch_fp64_peak(s->stream, static_cast<double*>(s->d_stats.ptr), blocks, threads, iters));
+        PIK_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+        PIK_CUDA(s, cudaStreamSynchronize(s->stream));
+        float ms = 0.f;
+        PIK_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        const double flops = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
+    return PIK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+"""GPU parity: the CUDA path through the C-ABI (libpik_b200.so) against the CPU oracle on the same
+seeded inputs.  Bar (BASELINE.json north_star): bit-exact converged / not-converged flags, converged
+joint angles within 1e-5 rad; because both sides share one arithmetic contract we additionally require
+bit-equal joint values, costs and iteration counts."""
+import numpy as np
+import pytest
+
+from oracle import orc
+from pick_ik_b200 import capi, robots
+
+pytestmark = pytest.mark.gpu
+
+TOL_RAD = 1e-5  # north_star tolerance for converged joint angles
+
+
+def both_params(**kw):
+    return orc.default_params(**kw), capi.default_params(**kw)
+
+
+@pytest.fixture(scope="module")
+def solvers():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            chain = robots.ROBOTS[name]()
+            cache[name] = (chain, orc.build_robot(chain.joint_desc()), capi.Solver(capi.Robot(chain)))
+        return cache[name]
+
+    yield get
+    for _, _, s in cache.values():
+        s.close()
+
+
+def random_configs(orobot, B, seed):
+    return np.stack([orc.random_configuration(orobot, seed, b) for b in range(B)])
+
+
+def check_solve(got, ref, label):
+    np.testing.assert_array_equal(got["error_code"], ref["error_code"], err_msg=f"{label}: flags")
+    ok = ref["error_code"] == 1
+    if ok.any():
+        assert np.abs(got["solution"][ok] - ref["solution"][ok]).max() <= TOL_RAD, f"{label}: joints"
+    np.testing.assert_array_equal(got["iterations"], ref["iterations"], err_msg=f"{label}: iterations")
+    np.testing.assert_array_equal(got["solution"], ref["solution"], err_msg=f"{label}: joints bit-equal")
+    np.testing.assert_array_equal(got["cost"], ref["cost"], err_msg=f"{label}: cost bit-equal")
+
+
+@pytest.mark.parametrize("name", ["rr", "panda", "ur5", "fetch", "skew6"])
+@pytest.mark.parametrize("goals", [False, True])
+def test_eval_cost_bit_exact(solvers, name, goals):
+    chain, orobot, solver = solvers(name)
+    kw = dict(center_joints_weight=0.3, avoid_joint_limits_weight=0.7, minimal_displacement_weight=0.2,
+              cost_threshold=0.05, position_threshold=0.2, orientation_threshold=0.3) if goals else {}
+    op, gp = both_params(**kw)
+    B = 3000
+    q = random_configs(orobot, B, 11)
+    q[::7] *= 1.7  # outside the limits as well
+    tq = random_configs(orobot, B, 12)
+    near = np.arange(B) % 3 == 0
+    tq[near] = q[near] + (0.01 if goals else 1e-5)  # some configurations that pass the solution test
+    goal = np.stack([orc.pose_from_fk(orobot, t) for t in tq])
+    seed = random_configs(orobot, B, 13)
+    c_ref, s_ref, tip_ref = orc.eval_cost_batch(orobot, op, goal, seed, q)
+    c, s, tip = solver.eval_cost(gp, goal, seed, q)
+    np.testing.assert_array_equal(c, c_ref)
+    np.testing.assert_array_equal(s, s_ref)
+    np.testing.assert_array_equal(tip, tip_ref)
+    if not goals:
+        assert 0 < s_ref.sum() < B
+
+
+@pytest.mark.parametrize("name", ["rr", "panda", "ur5", "fetch", "skew6"])
+def test_gd_local_parity(solvers, name):
+    chain, orobot, solver = solvers(name)
+    op, gp = both_params(mode="local")
+    B = 1500
+    seed = random_configs(orobot, B, 21)
+    rng = np.random.default_rng(5)
+    tq = seed + rng.uniform(-0.1, 0.1, seed.shape)
+    goal = np.stack([orc.pose_from_fk(orobot, t) for t in tq])
+    ref = orc.solve_batch(orobot, op, goal, seed)
+    got = solver.solve_batch(gp, goal, seed)
+    check_solve(got, ref, name)
+    assert 0 < (ref["error_code"] == 1).sum()
+
+
+def test_gd_local_options(solvers):
+    chain, orobot, solver = solvers("fetch")
+    B = 600
+    seed = random_configs(orobot, B, 31)
+    tq = seed + np.random.default_rng(6).uniform(-0.05, 0.05, seed.shape)
+    goal = np.stack([orc.pose_from_fk(orobot, t) for t in tq])
+    for kw in (dict(stop_optimization_on_valid_solution=0),
+               dict(return_approximate_solution=1, gd_max_iters=7),
+               dict(rotation_scale=0.0),
+               dict(position_scale=0.0),
+               dict(center_joints_weight=0.01, avoid_joint_limits_weight=0.01, minimal_displacement_weight=0.02,
+                    cost_threshold=0.01, position_threshold=0.01)):
+        op, gp = both_params(mode="local", **kw)
+        check_solve(solver.solve_batch(gp, goal, seed), orc.solve_batch(orobot, op, goal, seed), str(kw))
+
+
+MEMETIC_CASES = [
+    ("panda", dict(memetic_population_size=16), 300),
+    ("panda", dict(memetic_population_size=128), 200),
+    ("rr", dict(memetic_population_size=8, memetic_elite_size=2), 200),
+    ("ur5", dict(memetic_population_size=32, memetic_elite_size=5, memetic_max_generations=20), 150),
+    ("fetch", dict(memetic_population_size=64, center_joints_weight=0.01, avoid_joint_limits_weight=0.01,
+                   cost_threshold=0.01, position_threshold=0.01, memetic_max_generations=30), 150),
+    ("skew6", dict(memetic_population_size=24, memetic_elite_size=3, memetic_max_generations=25,
+                   minimal_displacement_weight=0.01, cost_threshold=0.05), 150),
+    ("panda", dict(memetic_population_size=4, memetic_elite_size=4, memetic_max_generations=10), 100),
+    ("panda", dict(memetic_population_size=20, memetic_elite_size=1, memetic_max_generations=10), 100),
+    ("fetch", dict(memetic_population_size=32, stop_optimization_on_valid_solution=0, memetic_max_generations=6), 100),
+    ("panda", dict(memetic_population_size=16, return_approximate_solution=1, memetic_max_generations=3), 100),
+]
+
+
+@pytest.mark.parametrize("name,kw,B", MEMETIC_CASES)
+def test_memetic_parity(solvers, name, kw, B):
+    chain, orobot, solver = solvers(name)
+    op, gp = both_params(mode="global", **kw)
+    goal = orc.make_targets(orobot, B)
+    if name == "panda":
+        seed = np.array(robots.PANDA_HOME)
+    else:
+        seed = random_configs(orobot, B, 41)
+    first = 1000
+    ref = orc.solve_batch(orobot, op, goal, seed, first_problem_index=first)
+    got = solver.solve_batch(gp, goal, seed, first_problem_index=first)
+    check_solve(got, ref, f"{name} {kw}")
+    st = solver.stats()
+    assert st.solved == (ref["error_code"] == 1).sum()
+    assert st.kernel_launches >= 1
+
+
+def test_memetic_seed_already_valid(solvers):
+    chain, orobot, solver = solvers("panda")
+    op, gp = both_params(mode="global")
+    q = random_configs(orobot, 64, 51)
+    goal = np.stack([orc.pose_from_fk(orobot, t) for t in q])
+    ref = orc.solve_batch(orobot, op, goal, q)
+    got = solver.solve_batch(gp, goal, q)
+    check_solve(got, ref, "valid seed")
+    assert (got["iterations"] == 0).all() and (got["error_code"] == 1).all()
+    np.testing.assert_array_equal(got["solution"], q)
+
+
+def test_sharding_invariance(solvers):
+    """A shard solved with first_problem_index reproduces the unsharded result (RNG keyed by the
+    global problem index)."""
+    chain, orobot, solver = solvers("panda")
+    _, gp = both_params(mode="global", memetic_population_size=32)
+    B = 128
+    goal = orc.make_targets(orobot, B)
+    seed = np.array(robots.PANDA_HOME)
+    whole = solver.solve_batch(gp, goal, seed)
+    lo = solver.solve_batch(gp, goal[:50], seed, first_problem_index=0)
+    hi = solver.solve_batch(gp, goal[50:], seed, first_problem_index=50)
+    for k in ("solution", "error_code", "cost", "iterations"):
+        np.testing.assert_array_equal(np.concatenate([lo[k], hi[k]]), whole[k])
+
+
+def test_empty_batch_and_errors(solvers):
+    chain, orobot, solver = solvers("panda")
+    gp = capi.default_params()
+    out = solver.solve_batch(gp, np.zeros((0, 7)), np.array(robots.PANDA_HOME))
+    assert out["solution"].shape == (0, 7)
+    bad = capi.default_params(memetic_elite_size=40, memetic_population_size=16)
+    with pytest.raises(capi.PikError):
+        solver.solve_batch(bad, np.zeros((1, 7)), np.array(robots.PANDA_HOME))
