@@ -103,6 +103,7 @@ typedef struct pik_stats {
     int64_t problem_generations;  /* sum over problems of generations executed */
     int64_t gd_steps;             /* GD step() executions */
     double device_ms;             /* CUDA-event time of the call's device work */
+    double generation_ms;         /* CUDA-event time summed over the generation kernel launches */
 } pik_stats;
 
 typedef struct pik_robot pik_robot;

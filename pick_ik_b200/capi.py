@@ -71,7 +71,7 @@ class Variable(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("problems", C.c_int64), ("solved", C.c_int64), ("generation_launches", C.c_int64),
                 ("kernel_launches", C.c_int64), ("problem_generations", C.c_int64), ("gd_steps", C.c_int64),
-                ("device_ms", C.c_double)]
+                ("device_ms", C.c_double), ("generation_ms", C.c_double)]
 
 
 _lib: Optional[C.CDLL] = None

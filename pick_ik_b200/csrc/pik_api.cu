@@ -33,7 +33,7 @@ struct pik_solver {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     int32_t* h_counters = nullptr;            // pinned [2]
     unsigned long long* h_stats = nullptr;    // pinned [4]
     // staging for PIK_MEM_HOST calls
@@ -237,6 +237,8 @@ int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_
     }
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev2);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev3);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_counters), 2 * sizeof(int32_t), cudaHostAllocDefault);
     if (e == cudaSuccess)
         e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_stats), 4 * sizeof(unsigned long long), cudaHostAllocDefault);
@@ -262,6 +264,8 @@ void pik_solver_destroy(pik_solver* s) {
     if (s->h_stats) cudaFreeHost(s->h_stats);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev2) cudaEventDestroy(s->ev2);
+    if (s->ev3) cudaEventDestroy(s->ev3);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -348,12 +352,17 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
         int list = 0;
         for (int gen = 0; gen < pr.max_generations && n_active > 0; ++gen) {
             PIK_CUDA(s, cudaMemsetAsync(sb.counters + (list ^ 1), 0, sizeof(int32_t), st));
+            PIK_CUDA(s, cudaEventRecord(s->ev2, st));
             PIK_CUDA(s, launch_memetic_generation(st, s->robot.dev, pr, sb, list, n_active));
+            PIK_CUDA(s, cudaEventRecord(s->ev3, st));
             s->stats.kernel_launches += 1;
             s->stats.generation_launches += 1;
             PIK_CUDA(s, cudaMemcpyAsync(s->h_counters + (list ^ 1), sb.counters + (list ^ 1), sizeof(int32_t),
                                         cudaMemcpyDeviceToHost, st));
             PIK_CUDA(s, cudaStreamSynchronize(st));
+            float gms = 0.f;
+            PIK_CUDA(s, cudaEventElapsedTime(&gms, s->ev2, s->ev3));
+            s->stats.generation_ms += gms;
             n_active = s->h_counters[list ^ 1];
             list ^= 1;
         }
