@@ -124,9 +124,10 @@ double orc_atan2(double y, double x) {
 /* ------------------------------------------------------------------------------------------
  * RNG.  The reference uses rsl::uniform_real / uniform_int over a thread-local std::mt19937 seeded
  * from random_device (src/robot.cpp:25-28, src/ik_memetic.cpp:131-159): unseeded, PARITY-UNPINNED.
- * We define Philox4x32-10 word streams: key = rng_seed, counter = (block, stream_lo, stream_hi,
- * problem).  uniform_real = 53-bit (as generate_canonical<double,53> over two 32-bit draws),
- * uniform_int = Lemire multiply-shift with rejection (as libstdc++ >= 11 for 32-bit URBGs).
+ * We define Philox4x32-10 word streams: key = rng_seed, counter = (block, individual,
+ * purpose << 28 | epoch, problem).  uniform_real = 53-bit (as generate_canonical<double,53> over two
+ * 32-bit draws), uniform_int = Lemire multiply-shift with rejection (as libstdc++ >= 11 for 32-bit
+ * URBGs).
  * ------------------------------------------------------------------------------------------ */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
@@ -145,53 +146,75 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-enum { STREAM_INIT = 1, STREAM_REPRODUCE = 2, STREAM_TARGET = 3 };
+enum { STREAM_INIT = 1, STREAM_REPRODUCE = 2, STREAM_TARGET = 3, STREAM_RANDOM_CHILD = 4 };
 
+/* A stream is identified by (seed, problem, purpose, epoch, individual); its words are addressed
+ * by block: counter = (block, individual, purpose << 28 | epoch, problem), key = seed.  Every
+ * consumer below reads FIXED (block, word) positions, so a draw never depends on how many words an
+ * earlier draw consumed -- which is what lets the CUDA kernels produce children in any order. */
 typedef struct {
     uint32_t key[2];
-    uint32_t ctr[4];
-    uint32_t buf[4];
-    int pos;
-} orc_rng;
+    uint32_t c1, c2, c3;
+} orc_stream;
 
-static void rng_init(orc_rng* r, uint64_t seed, uint32_t problem, uint32_t purpose, uint32_t epoch,
-                     uint32_t individual) {
-    r->key[0] = (uint32_t)seed;
-    r->key[1] = (uint32_t)(seed >> 32);
-    r->ctr[0] = 0;
-    r->ctr[1] = individual;
-    r->ctr[2] = (purpose << 28) | (epoch & 0x0fffffffu);
-    r->ctr[3] = problem;
-    r->pos = 4;
+static void stream_init(orc_stream* s, uint64_t seed, uint32_t problem, uint32_t purpose, uint32_t epoch,
+                        uint32_t individual) {
+    s->key[0] = (uint32_t)seed;
+    s->key[1] = (uint32_t)(seed >> 32);
+    s->c1 = individual;
+    s->c2 = (purpose << 28) | (epoch & 0x0fffffffu);
+    s->c3 = problem;
 }
 
-static uint32_t rng_u32(orc_rng* r) {
-    if (r->pos == 4) {
-        orc_philox4x32_10(r->ctr, r->key, r->buf);
-        r->ctr[0] += 1;
-        r->pos = 0;
-    }
-    return r->buf[r->pos++];
+static void stream_block(const orc_stream* s, uint32_t block, uint32_t out[4]) {
+    uint32_t ctr[4] = {block, s->c1, s->c2, s->c3};
+    orc_philox4x32_10(ctr, s->key, out);
 }
 
-/* u in [0,1), 53 bits: first word = low half */
-static double rng_unit(orc_rng* r) {
-    uint64_t lo = rng_u32(r);
-    uint64_t hi = rng_u32(r);
-    return (double)(((hi << 32) | lo) >> 11) * 0x1.0p-53;
+/* u in [0,1), 53 bits, as generate_canonical<double,53> over two 32-bit draws: first word = low half */
+static double unit_from_words(uint32_t lo, uint32_t hi) {
+    return (double)(((((uint64_t)hi) << 32) | (uint64_t)lo) >> 11) * 0x1.0p-53;
 }
 
 /* rsl::uniform_real(a, b): a + (b - a) * u */
-static double rng_uniform_real(orc_rng* r, double a, double b) { return a + (b - a) * rng_unit(r); }
+static double uniform_real_words(double a, double b, uint32_t lo, uint32_t hi) {
+    return a + (b - a) * unit_from_words(lo, hi);
+}
 
-/* rsl::uniform_int<size_t>(0, m - 1) */
-static uint32_t rng_uniform_int(orc_rng* r, uint32_t m) {
-    uint64_t prod = (uint64_t)rng_u32(r) * m;
+/* Word list feeding the parent-index draws of one child (rsl::uniform_int, ik_memetic.cpp:131-135):
+ * block0.w0..w3, block1.w2, block1.w3, then the words of blocks first_overflow, first_overflow+1, ... */
+typedef struct {
+    const orc_stream* s;
+    uint32_t head[6];
+    uint32_t ovf[4];
+    uint32_t ovf_block;
+    int pos;
+} orc_index_words;
+
+static uint32_t index_words_next(orc_index_words* w) {
+    uint32_t v;
+    if (w->pos < 6) {
+        v = w->head[w->pos];
+    } else {
+        int k = (w->pos - 6) & 3;
+        if (k == 0) {
+            stream_block(w->s, w->ovf_block, w->ovf);
+            w->ovf_block += 1;
+        }
+        v = w->ovf[k];
+    }
+    w->pos += 1;
+    return v;
+}
+
+/* rsl::uniform_int<size_t>(0, m - 1): Lemire multiply-shift with rejection (libstdc++ >= 11) */
+static uint32_t uniform_int_words(orc_index_words* w, uint32_t m) {
+    uint64_t prod = (uint64_t)index_words_next(w) * m;
     uint32_t low = (uint32_t)prod;
     if (low < m) {
         uint32_t thr = (0u - m) % m;
         while (low < thr) {
-            prod = (uint64_t)rng_u32(r) * m;
+            prod = (uint64_t)index_words_next(w) * m;
             low = (uint32_t)prod;
         }
     }
@@ -475,14 +498,17 @@ int orc_is_valid_configuration(const orc_robot* robot, const double* q) {
     return 1;
 }
 
-/* robot.cpp:23-30, 87-95 */
-static void set_random_valid_configuration(const orc_robot* robot, orc_rng* rng, double* config) {
+/* robot.cpp:23-30, 87-95.  Variable i draws its uniform from block i >> 1, word pair i & 1. */
+static void set_random_valid_configuration(const orc_robot* robot, const orc_stream* st, double* config) {
+    uint32_t w[4] = {0, 0, 0, 0};
     for (int i = 0; i < robot->n; ++i) {
         const orc_variable* v = &robot->vars[i];
+        if ((i & 1) == 0) stream_block(st, (uint32_t)(i >> 1), w);
+        uint32_t lo = w[2 * (i & 1)], hi = w[2 * (i & 1) + 1];
         if (v->bounded)
-            config[i] = rng_uniform_real(rng, v->min, v->max);
+            config[i] = uniform_real_words(v->min, v->max, lo, hi);
         else
-            config[i] = rng_uniform_real(rng, config[i] - M_PI, config[i] + M_PI);
+            config[i] = uniform_real_words(config[i] - M_PI, config[i] + M_PI, lo, hi);
     }
 }
 
@@ -753,10 +779,10 @@ static void init_population(orc_memetic* m, const double* initial_guess) {
         memset(ind, 0, sizeof(*ind));
         memcpy(ind->genes, initial_guess, m->n * sizeof(double));
         if (i > 0) {
-            orc_rng rng;
-            rng_init(&rng, m->cx.pb->params->rng_seed, m->problem_index, STREAM_INIT, m->init_epoch,
-                     (uint32_t)i);
-            set_random_valid_configuration(robot, &rng, ind->genes);
+            orc_stream st;
+            stream_init(&st, m->cx.pb->params->rng_seed, m->problem_index, STREAM_INIT, m->init_epoch,
+                        (uint32_t)i);
+            set_random_valid_configuration(robot, &st, ind->genes);
         }
         ind->fitness = cost_counted(&m->cx, ind->genes);
         ind->extinction = 1.0;
@@ -794,8 +820,11 @@ static void gradient_descent(orc_memetic* m, int i) {
     for (int k = 0; k < n; ++k) ind->gradient[k] = gradient[k];
 }
 
-/* ik_memetic.cpp:119-190.  RNG stream per child: (STREAM_REPRODUCE, generation, child index);
- * draw order: idxA, idxB (rejection loop), mix, then per gene r_A, r_B, r_mut, [r_amp]. */
+/* ik_memetic.cpp:119-190.  Stream of child i in generation g: (STREAM_REPRODUCE, g, i).  Fixed
+ * word layout: parent indices from the index word list (block0.w0-3, block1.w2-3, overflow blocks
+ * 2n+2, ...), idxA first, then idxB's rejection loop; mix = block1.(w0,w1); gene j: r_A =
+ * block(2+2j).(w0,w1), r_B = block(2+2j).(w2,w3) (the reference leaves the order of these two
+ * draws to the compiler: fixed here), r_mut = block(3+2j).(w0,w1), r_amp = block(3+2j).(w2,w3). */
 static void reproduce(orc_memetic* m, uint32_t generation) {
     const orc_robot* robot = m->cx.pb->robot;
     const int n = m->n;
@@ -806,29 +835,41 @@ static void reproduce(orc_memetic* m, uint32_t generation) {
 
     for (int i = m->E; i < m->P; ++i) {
         orc_individual* child = &m->pop[i];
-        orc_rng rng;
-        rng_init(&rng, m->cx.pb->params->rng_seed, m->problem_index, STREAM_REPRODUCE, generation,
-                 (uint32_t)i);
         if (pool_size > 0) {
-            uint32_t idxA = rng_uniform_int(&rng, (uint32_t)pool_size);
+            orc_stream st;
+            stream_init(&st, m->cx.pb->params->rng_seed, m->problem_index, STREAM_REPRODUCE, generation,
+                        (uint32_t)i);
+            uint32_t b0[4], b1[4];
+            stream_block(&st, 0, b0);
+            stream_block(&st, 1, b1);
+            orc_index_words iw;
+            iw.s = &st;
+            iw.head[0] = b0[0]; iw.head[1] = b0[1]; iw.head[2] = b0[2]; iw.head[3] = b0[3];
+            iw.head[4] = b1[2]; iw.head[5] = b1[3];
+            iw.ovf_block = (uint32_t)(2 * n + 2);
+            iw.pos = 0;
+            uint32_t idxA = uniform_int_words(&iw, (uint32_t)pool_size);
             uint32_t idxB = idxA;
-            while (idxB == idxA && pool_size > 1) idxB = rng_uniform_int(&rng, (uint32_t)pool_size);
+            while (idxB == idxA && pool_size > 1) idxB = uniform_int_words(&iw, (uint32_t)pool_size);
             const int ia = pool[idxA], ib = pool[idxB];
             const orc_individual* parentA = &m->pop[ia];
             const orc_individual* parentB = &m->pop[ib];
 
             double extinction = 0.5 * (parentA->extinction + parentB->extinction);
             double mutation_prob = extinction * (1.0 - inverse_gene_size) + inverse_gene_size;
-            double mix_ratio = rng_uniform_real(&rng, 0.0, 1.0);
+            double mix_ratio = uniform_real_words(0.0, 1.0, b1[0], b1[1]);
             for (int j = 0; j < n; ++j) {
                 const orc_variable* joint = &robot->vars[j];
+                uint32_t wa[4], wm[4];
+                stream_block(&st, (uint32_t)(2 + 2 * j), wa);
+                stream_block(&st, (uint32_t)(3 + 2 * j), wm);
                 double gene = mix_ratio * parentA->genes[j] + (1.0 - mix_ratio) * parentB->genes[j];
-                double rA = rng_uniform_real(&rng, 0.0, 1.0);
-                double rB = rng_uniform_real(&rng, 0.0, 1.0);
+                double rA = uniform_real_words(0.0, 1.0, wa[0], wa[1]);
+                double rB = uniform_real_words(0.0, 1.0, wa[2], wa[3]);
                 gene += rA * parentA->gradient[j] + rB * parentB->gradient[j];
                 double original_gene = gene;
-                if (rng_uniform_real(&rng, 0.0, 1.0) < mutation_prob)
-                    gene += extinction * joint->half_span * rng_uniform_real(&rng, -1.0, 1.0);
+                if (uniform_real_words(0.0, 1.0, wm[0], wm[1]) < mutation_prob)
+                    gene += extinction * joint->half_span * uniform_real_words(-1.0, 1.0, wm[2], wm[3]);
                 gene = orc_clamp_to_limits(joint, gene);
                 child->genes[j] = gene;
                 child->gradient[j] = gene - original_gene;
@@ -852,7 +893,10 @@ static void reproduce(orc_memetic* m, uint32_t generation) {
                     }
             }
         } else {
-            set_random_valid_configuration(robot, &rng, child->genes);
+            orc_stream st;
+            stream_init(&st, m->cx.pb->params->rng_seed, m->problem_index, STREAM_RANDOM_CHILD, generation,
+                        (uint32_t)i);
+            set_random_valid_configuration(robot, &st, child->genes);
             child->fitness = cost_counted(&m->cx, child->genes);
             for (int j = 0; j < n; ++j) child->gradient[j] = 0.0;
         }
@@ -1060,11 +1104,14 @@ void orc_eval_cost_batch(const orc_robot* robot, const orc_params* params, int64
 /* SURVEY 8(d) synthetic inputs: q* ~ U(min, max) per variable (unbounded: U(-pi, pi)) */
 void orc_random_configuration(const orc_robot* robot, uint64_t gen_seed, uint32_t problem_index,
                               double* q) {
-    orc_rng rng;
-    rng_init(&rng, gen_seed, problem_index, STREAM_TARGET, 0, 0);
+    orc_stream st;
+    stream_init(&st, gen_seed, problem_index, STREAM_TARGET, 0, 0);
+    uint32_t w[4] = {0, 0, 0, 0};
     for (int i = 0; i < robot->n; ++i) {
         const orc_variable* v = &robot->vars[i];
-        q[i] = v->bounded ? rng_uniform_real(&rng, v->min, v->max) : rng_uniform_real(&rng, -M_PI, M_PI);
+        if ((i & 1) == 0) stream_block(&st, (uint32_t)(i >> 1), w);
+        uint32_t lo = w[2 * (i & 1)], hi = w[2 * (i & 1) + 1];
+        q[i] = v->bounded ? uniform_real_words(v->min, v->max, lo, hi) : uniform_real_words(-M_PI, M_PI, lo, hi);
     }
 }
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpik_b200.so")
 SOURCES = ["pik_kernels.cu", "pik_api.cu"]
-HEADERS = ["pik_device.cuh", "pik_kernels.cuh", "pik_host_robot.h", os.path.join("..", "..", "include", "pik.h")]
+HEADERS = ["pik_device.cuh", "pik_kernels.cuh", "pik_types.h", "pik_host_robot.h", os.path.join("..", "..", "include", "pik.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "--fmad=false",

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 
@@ -77,6 +78,19 @@ void release(DeviceArray& a) {
 }
 
 bool finite_ge(double v, double lo) { return v == v && v >= lo; }
+
+// The robot table and the solver parameters live in __constant__ memory, one copy per device: calls that
+// launch kernels are serialised per process.
+std::mutex g_launch_mutex;
+
+// Active-problem count at or below which a generation runs in latency mode (several lanes per elite).
+int64_t wide_threshold() {
+    static const int64_t v = [] {
+        const char* e = std::getenv("PIK_WIDE_THRESHOLD");
+        return e ? std::atoll(e) : (int64_t)6144;
+    }();
+    return v;
+}
 
 }  // namespace
 
@@ -320,7 +334,7 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
     const bool global = params->mode == PIK_MODE_GLOBAL;
     if (global) {
         const size_t F = 2 * (size_t)n + 2;
-        if ((rc = ensure(s, s->d_pop, 2 * (size_t)B * F * P * 8)) || (rc = ensure(s, s->d_order, (size_t)B * P * 2)) ||
+        if ((rc = ensure(s, s->d_pop, 2 * (size_t)B * F * P * 8)) || (rc = ensure(s, s->d_order, 2 * (size_t)B * P * 2)) ||
             (rc = ensure(s, s->d_hdr, (size_t)B * (n + 2) * 8)) || (rc = ensure(s, s->d_meta, (size_t)B * sizeof(ProblemMeta))) ||
             (rc = ensure(s, s->d_active, 2 * (size_t)B * 4)) || (rc = ensure(s, s->d_counters, 2 * 4)))
             return rc;
@@ -333,18 +347,20 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
     }
 
     cudaStream_t st = s->stream;
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
     PIK_CUDA(s, cudaEventRecord(s->ev0, st));
+    PIK_CUDA(s, upload_constants(st, s->robot.dev, pr));
     if (memory == PIK_MEM_HOST) {
         PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
         PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
     }
     PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 4 * sizeof(unsigned long long), st));
     if (!global) {
-        PIK_CUDA(s, launch_gd_local(st, s->robot.dev, pr, sb));
+        PIK_CUDA(s, launch_gd_local(st, n, sb));
         s->stats.kernel_launches += 1;
     } else {
         PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, 2 * sizeof(int32_t), st));
-        PIK_CUDA(s, launch_memetic_init(st, s->robot.dev, pr, sb));
+        PIK_CUDA(s, launch_memetic_init(st, n, P, pr.E, sb));
         s->stats.kernel_launches += 1;
         PIK_CUDA(s, cudaMemcpyAsync(s->h_counters, sb.counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         PIK_CUDA(s, cudaStreamSynchronize(st));
@@ -353,7 +369,8 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
         for (int gen = 0; gen < pr.max_generations && n_active > 0; ++gen) {
             PIK_CUDA(s, cudaMemsetAsync(sb.counters + (list ^ 1), 0, sizeof(int32_t), st));
             PIK_CUDA(s, cudaEventRecord(s->ev2, st));
-            PIK_CUDA(s, launch_memetic_generation(st, s->robot.dev, pr, sb, list, n_active));
+            const int lanes = n_active <= wide_threshold() ? memetic_max_lanes_per_elite(pr.E) : 1;
+            PIK_CUDA(s, launch_memetic_generation(st, n, P, pr.E, sb, list, n_active, lanes));
             PIK_CUDA(s, cudaEventRecord(s->ev3, st));
             s->stats.kernel_launches += 1;
             s->stats.generation_launches += 1;
@@ -400,8 +417,11 @@ int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const doub
     PIK_CUDA(s, cudaSetDevice(s->device));
     const DevParams pr = make_dev_params(*params);
     cudaStream_t st = s->stream;
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
+    PIK_CUDA(s, upload_constants(st, s->robot.dev, pr));
     if (memory == PIK_MEM_DEVICE) {
-        PIK_CUDA(s, launch_eval_cost(st, s->robot.dev, pr, B, goal_pose, seed, seed_stride, q, cost, is_solution, tip_pose));
+        PIK_CUDA(s, launch_eval_cost(st, n, B, goal_pose, seed, seed_stride, q, cost, is_solution, tip_pose));
+        PIK_CUDA(s, cudaStreamSynchronize(st));
         return PIK_OK;
     }
     const size_t seed_elems = seed_stride ? (size_t)B * n : (size_t)n;
@@ -412,7 +432,7 @@ int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const doub
     PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
     PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
     PIK_CUDA(s, cudaMemcpyAsync(s->d_q.ptr, q, (size_t)B * n * 8, cudaMemcpyHostToDevice, st));
-    PIK_CUDA(s, launch_eval_cost(st, s->robot.dev, pr, B, static_cast<double*>(s->d_goal.ptr),
+    PIK_CUDA(s, launch_eval_cost(st, n, B, static_cast<double*>(s->d_goal.ptr),
                                  static_cast<double*>(s->d_seed.ptr), seed_stride, static_cast<double*>(s->d_q.ptr),
                                  cost ? static_cast<double*>(s->d_cost.ptr) : nullptr,
                                  is_solution ? static_cast<int32_t*>(s->d_issol.ptr) : nullptr,

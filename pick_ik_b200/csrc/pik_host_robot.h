@@ -10,7 +10,7 @@
 #include <cstring>
 
 #include "../../include/pik.h"
-#include "pik_device.cuh"
+#include "pik_types.h"
 
 namespace pik {
 

@@ -6,99 +6,86 @@
 //   memetic_generation_kernel  one iteration of ik_memetic_impl's loop          (src/ik_memetic.cpp:228-269):
 //                              gradientDescent on the elites, reproduce, sortPopulation, solution test, checkWipeout
 //
-// Mapping.  The unit of parallel work is one cost evaluation chain (FK walk + pose/goal costs), which is a
-// serial FP64 dependency chain.  One CTA owns G problems.  Elite local search runs one GD instance per
-// thread (G*E threads), so every lane of a warp carries a whole finite-difference + line-search step of
-// its own elite; reproduction runs one child per thread over the flattened (problem, child) items with the
-// sequential mating-pool semantics recovered by speculation rounds; the sort is a rank computation that
-// permutes a slot-index row, never the individuals.  All arithmetic is binary64 with --fmad=false (see
-// pik_device.cuh) and is bit-identical to oracle/pik_oracle.c.
+// Mapping.  The unit of work is one cost evaluation (FK chain walk + pose/goal costs): a serial FP64
+// dependency chain of ~10^3 operations.  Every WARP is autonomous -- it owns PW problems end to end and
+// never meets a block barrier:
+//   * elite local search: one GD instance per lane (L = 1), every lane carrying whole finite-difference
+//     + line-search steps of its own elite; or, when the batch has nearly drained and latency is all that
+//     is left, L lanes per elite with the 2n finite-difference evaluations of a step spread over them;
+//   * reproduction: the warp walks each problem's children in windows of 32 (one child per lane); the
+//     sequential mating-pool semantics of the reference are kept by committing a window only up to the
+//     first child that removes a parent and restarting after it with the shrunken pool;
+//   * the sort permutes a slot-index row, never the individuals (top-E selection by warp reductions;
+//     a full rank computation only for robots with unbounded variables, which need the whole order).
+// All arithmetic is binary64 with --fmad=false (see pik_device.cuh) and is bit-identical to
+// oracle/pik_oracle.c whatever the mapping.
 #include "pik_kernels.cuh"
 
 #include <limits.h>
+
+#include "pik_device.cuh"
 
 namespace pik {
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kWarpsPerBlock = 4;
+constexpr int kThreads = 32 * kWarpsPerBlock;
+constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-
-// Shared-memory carve of the memetic kernels (same arithmetic on host in memetic_shape()).
-struct MemSmem {
-    uint16_t* ord;   // [G][P]   slot of population position i
-    double* el;      // [G][E][2n+2] the mating pool candidates: genes, gradient, fitness, extinction
-    double* cg;      // [n][T]   one configuration column per thread (child genes / new elites)
-    double* uni;     // phase 1: GD arrays [5n][T]; afterwards fit [G][P] + par [G][P][2]
-    double* fit;     // [G][P]   fitness by population position (aliases uni)
-    uint8_t* par;    // [G][P][2] parent elite indices of each child (aliases uni)
-    double* goal;    // [G][7]
-    int* pidx;       // [G] problem index or -1
-    int* pool_size;  // [G]
-    int* start;      // [G] first uncommitted child
-    int* first_rem;  // [G] lowest child that removes a parent in this round
-    int* flag;       // [G] wipeout / (re)initialise
-    int* top;        // [G][E+1] positions of rank 0..E-1 and rank P-1
-    int* pool;       // [G][E]
-    int* misc;       // [4]
+// Per-warp shared memory.  Columns (stride kS = 32): q, g, best [n] each, sc [2n].
+struct WarpSmem {
+    double* q;
+    double* g;
+    double* best;
+    double* sc;
+    double* cs;    // [2n][16] finite-difference / line-search costs of the lane-parallel GD step
+    double* fit;   // [P] fitness by population position of the problem being reproduced / sorted
+    double* goal;  // [32][7]
+    double* efit;  // [32] elite fitness by column
+    double* eext;  // [32] elite extinction by column
+    double* f0s;   // [32] best_curr fitness per problem
+    int* pool;     // [32]
+    int* top;      // [33] positions of rank 0..E-1 and (at [E]) rank P-1
+    int* pidx;     // [32] problem index per problem slot, or -1
+    int* flag;     // [32]
+    int* ctl;      // [4]
 };
 
-__host__ __device__ inline size_t memetic_smem_layout(int n, int P, int E, int T, int G, size_t* off) {
-    const size_t F = 2 * (size_t)n + 2;
-    size_t o = 0;
-    off[0] = o; o += ((size_t)G * P * 2 + 15) & ~size_t(15);
-    off[1] = o; o += (size_t)G * E * F * 8;
-    off[2] = o; o += (size_t)n * T * 8;
-    const size_t gd = 5 * (size_t)n * T * 8;
-    const size_t fp = (size_t)G * P * 8 + (((size_t)G * P * 2 + 15) & ~size_t(15));
-    off[3] = o; o += gd > fp ? gd : fp;
-    off[4] = o; o += (size_t)G * 7 * 8;
-    off[5] = o; o += (size_t)G * 4;              // pidx
-    off[6] = o; o += (size_t)G * 4;              // pool_size
-    off[7] = o; o += (size_t)G * 4;              // start
-    off[8] = o; o += (size_t)G * 4;              // first_rem
-    off[9] = o; o += (size_t)G * 4;              // flag
-    off[10] = o; o += (size_t)G * (E + 1) * 4;   // top
-    off[11] = o; o += (size_t)G * E * 4;         // pool
-    off[12] = o; o += 16;                        // misc
-    return (o + 15) & ~size_t(15);
+__host__ __device__ inline size_t warp_smem_bytes(int n, int P) {
+    size_t d = (size_t)5 * n * kS + (size_t)2 * n * 16 + (size_t)P + 32 * 7 + 3 * 32;
+    size_t i = 32 + 33 + 32 + 32 + 4;
+    return ((d * 8 + i * 4) + 15) & ~size_t(15);
 }
 
-__device__ __forceinline__ MemSmem carve(unsigned char* base, int n, int P, int E, int T, int G) {
-    size_t off[13];
-    memetic_smem_layout(n, P, E, T, G, off);
-    MemSmem L;
-    L.ord = reinterpret_cast<uint16_t*>(base + off[0]);
-    L.el = reinterpret_cast<double*>(base + off[1]);
-    L.cg = reinterpret_cast<double*>(base + off[2]);
-    L.uni = reinterpret_cast<double*>(base + off[3]);
-    L.fit = L.uni;
-    L.par = reinterpret_cast<uint8_t*>(base + off[3] + (size_t)G * P * 8);
-    L.goal = reinterpret_cast<double*>(base + off[4]);
-    L.pidx = reinterpret_cast<int*>(base + off[5]);
-    L.pool_size = reinterpret_cast<int*>(base + off[6]);
-    L.start = reinterpret_cast<int*>(base + off[7]);
-    L.first_rem = reinterpret_cast<int*>(base + off[8]);
-    L.flag = reinterpret_cast<int*>(base + off[9]);
-    L.top = reinterpret_cast<int*>(base + off[10]);
-    L.pool = reinterpret_cast<int*>(base + off[11]);
-    L.misc = reinterpret_cast<int*>(base + off[12]);
-    return L;
+__device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P) {
+    WarpSmem W;
+    double* d = reinterpret_cast<double*>(base);
+    W.q = d; d += (size_t)n * kS;
+    W.g = d; d += (size_t)n * kS;
+    W.best = d; d += (size_t)n * kS;
+    W.sc = d; d += (size_t)2 * n * kS;
+    W.cs = d; d += (size_t)2 * n * 16;
+    W.fit = d; d += P;
+    W.goal = d; d += 32 * 7;
+    W.efit = d; d += 32;
+    W.eext = d; d += 32;
+    W.f0s = d; d += 32;
+    int* ip = reinterpret_cast<int*>(d);
+    W.pool = ip; ip += 32;
+    W.top = ip; ip += 33;
+    W.pidx = ip; ip += 32;
+    W.flag = ip; ip += 32;
+    W.ctl = ip;
+    return W;
 }
 
 __device__ __forceinline__ double* pop_ptr(const SolveBuffers& sb, int buf, int64_t b, int n, int P) {
     return sb.pop + (((size_t)buf * (size_t)sb.B + (size_t)b) * (size_t)(2 * n + 2)) * (size_t)P;
 }
 
-__device__ __forceinline__ void load_goal(const double* g7, Goal& g) {
-    g.t[0] = g7[0]; g.t[1] = g7[1]; g.t[2] = g7[2];
-    g.q[0] = g7[3]; g.q[1] = g7[4]; g.q[2] = g7[5]; g.q[3] = g7[6];
-}
-
-__device__ __forceinline__ void store_goal(double* g7, const Goal& g) {
-    g7[0] = g.t[0]; g7[1] = g.t[1]; g7[2] = g.t[2];
-    g7[3] = g.q[0]; g7[4] = g.q[1]; g7[5] = g.q[2]; g7[6] = g.q[3];
+__device__ __forceinline__ uint16_t* order_ptr(const SolveBuffers& sb, int buf, int64_t b, int P) {
+    return sb.order + ((size_t)buf * (size_t)sb.B + (size_t)b) * (size_t)P;
 }
 
 // Plugin output mapping (src/pick_ik_plugin.cpp:209-217): genes on success, the seed otherwise.
@@ -112,24 +99,33 @@ __device__ __forceinline__ void write_result(const SolveBuffers& sb, int n, int6
 }
 
 // -----------------------------------------------------------------------------------------------
-// Batched FK + cost + solution test, one configuration per thread
+// Batched FK + cost + solution test, one configuration per lane
 // -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) eval_cost_kernel(const __grid_constant__ DevRobot rb,
-                                                             const __grid_constant__ DevParams pr, int64_t B,
-                                                             const double* __restrict__ goal_pose,
+__global__ void __launch_bounds__(kThreads) eval_cost_kernel(int64_t B, const double* __restrict__ goal_pose,
                                                              const double* __restrict__ seed, int64_t seed_stride,
                                                              const double* __restrict__ q, double* cost,
                                                              int32_t* is_solution, double* tip_pose) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = c_rb.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* col = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (n + 7) * kS + lane;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    Goal goal;
-    goal_from_pose(goal_pose + 7 * b, goal);
+    double g7[7];
+    goal_from_pose(goal_pose + 7 * b, g7);
     const double* sd = seed + b * seed_stride;
-    const ConfigView cv = plain_view(q + b * rb.n, 1);
+    for (int j = 0; j < n; ++j) col[j * kS] = q[b * n + j];
+    // tip frame: walk here (the tip pose is an output of this kernel only)
+    const ConfigView cv{col, nullptr, kViewPlain, -1, 0.0};
     Frame F;
-    fk_full(rb, cv, F, nullptr);
-    if (cost) cost[b] = total_cost(rb, pr, goal, F, cv, sd);
-    if (is_solution) is_solution[b] = solution_test(rb, pr, goal, F, cv, sd) ? 1 : 0;
+    frame_load_origin(F, 0);
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) walk_joint(F, j, j > 0, cv.at(j), true, nullptr, nullptr);
+    if (c_rb.has_tip) frame_mul_const(F, c_rb.tip_R, c_rb.tip_t);
+    double aux[5];
+    const double c = total_cost(g7, F, cv, sd, aux);
+    if (cost) cost[b] = c;
+    if (is_solution) is_solution[b] = solution_from_aux(aux) ? 1 : 0;
     if (tip_pose) {
         double* tp = tip_pose + 7 * b;
         tp[0] = F.t[0]; tp[1] = F.t[1]; tp[2] = F.t[2];
@@ -138,63 +134,56 @@ __global__ void __launch_bounds__(kThreads) eval_cost_kernel(const __grid_consta
 }
 
 // -----------------------------------------------------------------------------------------------
-// ik_gradient (src/ik_gradient.cpp:96-139), one problem per thread, whole loop on chip
+// ik_gradient (src/ik_gradient.cpp:96-139), one problem per lane, whole loop on chip
 // -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constant__ DevRobot rb,
-                                                            const __grid_constant__ DevParams pr,
-                                                            const __grid_constant__ SolveBuffers sb) {
+__global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constant__ SolveBuffers sb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sm = reinterpret_cast<double*>(smem_raw);
-    const int n = rb.n;
-    const int T = kThreads;
-    const int tid = threadIdx.x;
-    const int64_t b = (int64_t)blockIdx.x * T + tid;
+    const int n = c_rb.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (5 * n + 7) * kS;
+    const int64_t b = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (b >= sb.B) return;
-    GdState st{sm + tid, sm + (size_t)n * T + tid, sm + 2 * (size_t)n * T + tid, sm + 3 * (size_t)n * T + tid, T, 0.0, 0.0};
+    GdState st{base + lane, base + (size_t)n * kS + lane, base + (size_t)2 * n * kS + lane,
+               base + (size_t)3 * n * kS + lane, 0.0, 0.0};
+    double* g7 = base + (size_t)5 * n * kS + lane * 7;  // 7 contiguous doubles per lane
     const double* sd = sb.seed + b * sb.seed_stride;
     for (int j = 0; j < n; ++j) {
-        st.q[j * T] = sd[j];
-        st.best[j * T] = sd[j];
-        st.g[j * T] = 0.0;
+        st.q[j * kS] = sd[j];
+        st.best[j * kS] = sd[j];
+        st.g[j * kS] = 0.0;
     }
-    Goal goal;
-    goal_from_pose(sb.goal_pose + 7 * b, goal);
-    const ConfigView cvq = plain_view(st.q, T);
-    Frame F;
-    fk_full(rb, cvq, F, st.sc);
+    goal_from_pose(sb.goal_pose + 7 * b, g7);
+    double aux[5];
+    const double c0 = eval_chain(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, aux);
     bool found = false;
     int iters = 0;
     unsigned long long steps = 0;
-    double out_cost;
-    if (pr.stop_on_valid && solution_test(rb, pr, goal, F, cvq, sd)) {  // ik_gradient.cpp:102-104
+    double out_cost = c0;
+    if (c_pr.stop_on_valid && solution_from_aux(aux)) {  // ik_gradient.cpp:102-104
         found = true;
-        out_cost = total_cost(rb, pr, goal, F, cvq, sd);
     } else {
-        st.local_cost = st.best_cost = total_cost(rb, pr, goal, F, cvq, sd);  // GradientIk::from
+        st.local_cost = st.best_cost = c0;  // GradientIk::from
         double previous_cost = 0.0;
-        while (iters < pr.gd_max_iters) {
-            Frame FL;
-            const bool improved = gd_step(rb, pr, goal, st, sd, FL);
+        while (iters < c_pr.gd_max_iters) {
+            const bool improved = gd_step(st, g7, sd, aux);
             ++steps;
-            // best == local when improved, so FL is the tip frame of best (ik_gradient.cpp:117-121)
-            if (improved && pr.stop_on_valid && solution_test(rb, pr, goal, FL, cvq, sd)) {
+            // best == local when improved, so aux describes best (ik_gradient.cpp:117-121)
+            if (improved && c_pr.stop_on_valid && solution_from_aux(aux)) {
                 found = true;
                 break;
             }
-            if (fabs(st.local_cost - previous_cost) <= pr.min_cost_delta) break;  // ik_gradient.cpp:123-125
+            if (fabs(st.local_cost - previous_cost) <= c_pr.min_cost_delta) break;  // ik_gradient.cpp:123-125
             previous_cost = st.local_cost;
             ++iters;
         }
-        if (!found && !pr.stop_on_valid) {  // ik_gradient.cpp:130-132
-            const ConfigView cvb = plain_view(st.best, T);
-            Frame FB;
-            fk_full(rb, cvb, FB, nullptr);
-            found = solution_test(rb, pr, goal, FB, cvb, sd);
+        if (!found && !c_pr.stop_on_valid) {  // ik_gradient.cpp:130-132
+            eval_chain(st.best, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
+            found = solution_from_aux(aux);
         }
-        if (!found && pr.approx) found = true;  // ik_gradient.cpp:134-136
+        if (!found && c_pr.approx) found = true;  // ik_gradient.cpp:134-136
         out_cost = st.best_cost;
     }
-    write_result(sb, n, b, found, st.best, T, sd, out_cost, iters);
+    write_result(sb, n, b, found, st.best, kS, sd, out_cost, iters);
     if (sb.stats) {
         atomicAdd(&sb.stats[1], steps);
         if (found) atomicAdd(&sb.stats[2], 1ull);
@@ -203,103 +192,104 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
 }
 
 // -----------------------------------------------------------------------------------------------
-// initPopulation (src/ik_memetic.cpp:93-117) for every problem p of the CTA with flag[p] != 0, from
-// the best genes in hdr[b], into population buffer wbuf.  Elite 0 keeps the genes; elites 1..E-1 are
-// random valid configurations seeded from them; children are copies whose fitness equals the best
-// fitness (identical genes, deterministic cost), so only E - 1 evaluations are new.  Extinctions are
-// computed on this unsorted population as the reference does.  Must be called by all threads.
+// initPopulation (src/ik_memetic.cpp:93-117) for every problem slot k of the warp with flag[k] != 0, from
+// the best genes in hdr[b], into the population buffer the problem's next generation reads.  Elite 0
+// keeps the genes; elites 1..E-1 are random valid configurations seeded from them; children are copies
+// whose fitness equals the best fitness (identical genes, deterministic cost), so only E - 1 evaluations
+// are new.  Extinctions are computed on this unsorted population as the reference does.  Called by all
+// lanes of the warp.
 // -----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void init_population_coop(const DevRobot& rb, const DevParams& pr, const SolveBuffers& sb,
-                                                     const MemSmem& L, int T, int G, int tid) {
-    const int n = rb.n, P = pr.P, E = pr.E;
-    const int p_e = tid / E, e = tid % E;
-    const bool elite_thread = tid < G * E && L.flag[p_e] != 0;
+__device__ __forceinline__ void init_population_warp(const SolveBuffers& sb, const WarpSmem& W, int PW, int lane) {
+    const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
+    const int k_e = lane / E, e = lane % E;
+    const bool elite_lane = lane < PW * E && W.flag[k_e] != 0;
     int64_t b = -1;
     double* dst = nullptr;
     const double* hdr = nullptr;
-    if (elite_thread) {
-        b = L.pidx[p_e];
+    if (elite_lane) {
+        b = W.pidx[k_e];
         const ProblemMeta m = sb.meta[b];
         dst = pop_ptr(sb, m.iter & 1, b, n, P);
         hdr = sb.hdr + (size_t)b * (n + 2);
-        double* col = L.cg + tid;
-        for (int j = 0; j < n; ++j) col[j * T] = hdr[j];
+        double* col = W.q + lane;
+        for (int j = 0; j < n; ++j) col[j * kS] = hdr[j];
         double f = hdr[n];
         if (e > 0) {
-            Rng rng;
-            rng_init(rng, pr.seed_lo, pr.seed_hi, (uint32_t)(sb.first_problem_index + b), kStreamInit,
-                     (uint32_t)m.init_epoch, (uint32_t)e);
-            random_valid_configuration(rb, rng, col, T);
-            Goal goal;
-            load_goal(L.goal + 7 * p_e, goal);
-            f = cost_full(rb, pr, goal, plain_view(col, T), sb.seed + b * sb.seed_stride, nullptr);
+            const Stream st = make_stream((uint32_t)(sb.first_problem_index + b), kStreamInit, (uint32_t)m.init_epoch,
+                                          (uint32_t)e);
+            random_valid_configuration(st, col);
+            f = eval_chain(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k_e,
+                           sb.seed + b * sb.seed_stride, nullptr);
         }
-        L.fit[p_e * P + e] = f;
+        W.efit[lane] = f;
         for (int j = 0; j < n; ++j) {
-            dst[(size_t)j * P + e] = col[j * T];
+            dst[(size_t)j * P + e] = col[j * kS];
             dst[(size_t)(n + j) * P + e] = 0.0;
         }
         dst[(size_t)(2 * n) * P + e] = f;
     }
-    __syncthreads();
-    for (int item = tid; item < G * P; item += T) {
-        const int p = item / P, i = item % P;
-        if (!L.flag[p]) continue;
-        const int64_t bb = L.pidx[p];
-        sb.order[(size_t)bb * P + i] = (uint16_t)i;
-        if (i >= E && rb.any_unbounded) {
+    __syncwarp();
+    for (int k = 0; k < PW; ++k) {
+        if (!W.flag[k]) continue;
+        const int64_t bb = W.pidx[k];
+        const int buf = sb.meta[bb].iter & 1;
+        uint16_t* ord = order_ptr(sb, buf, bb, P);
+        for (int i = lane; i < P; i += 32) ord[i] = (uint16_t)i;
+        if (c_rb.any_unbounded) {  // children = copies of the genes; only ever read to seed a random individual
             const double* h = sb.hdr + (size_t)bb * (n + 2);
-            double* d = pop_ptr(sb, sb.meta[bb].iter & 1, bb, n, P);
-            for (int j = 0; j < n; ++j) d[(size_t)j * P + i] = h[j];
+            double* d = pop_ptr(sb, buf, bb, n, P);
+            for (int i = E + lane; i < P; i += 32)
+                for (int j = 0; j < n; ++j) d[(size_t)j * P + i] = h[j];
         }
     }
-    if (elite_thread) {
-        const double f0 = L.fit[p_e * P];
-        const double fl = (P > E) ? hdr[n] : L.fit[p_e * P + P - 1];
+    if (elite_lane) {
+        const double f0 = W.efit[k_e * E];
+        const double fl = (P > E) ? hdr[n] : W.efit[k_e * E + E - 1];
         const double grading = (double)e / (double)(P - 1);  // ik_memetic.cpp:36-39
-        dst[(size_t)(2 * n + 1) * P + e] = (L.fit[p_e * P + e] + f0 * (grading - 1.0)) / fl;
+        dst[(size_t)(2 * n + 1) * P + e] = (W.efit[lane] + f0 * (grading - 1.0)) / fl;
+        if (e == 0) {
+            sb.meta[b].has_prev = 0;  // previous_fitness_.reset()
+            sb.meta[b].init_epoch += 1;
+        }
     }
-    __syncthreads();
-    if (elite_thread && e == 0) {
-        sb.meta[b].has_prev = 0;  // previous_fitness_.reset()
-        sb.meta[b].init_epoch += 1;
-    }
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_constant__ DevRobot rb,
-                                                                const __grid_constant__ DevParams pr,
-                                                                const __grid_constant__ SolveBuffers sb, int G) {
+__global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_constant__ SolveBuffers sb, int PW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = rb.n, P = pr.P, E = pr.E;
-    const int T = kThreads;
-    const int tid = threadIdx.x;
-    const MemSmem L = carve(smem_raw, n, P, E, T, G);
-    const int64_t base = (int64_t)blockIdx.x * G;
-    if (tid < G) {
-        const int64_t b = base + tid;
-        L.pidx[tid] = b < sb.B ? (int)b : -1;
-        L.flag[tid] = 0;
+    const int n = c_rb.n, P = c_pr.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P), n, P);
+    const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * PW;
+    if (base >= sb.B) return;
+    bool keep = false;
+    int64_t b = -1;
+    if (lane < PW) {
+        b = base + lane;
+        W.pidx[lane] = b < sb.B ? (int)b : -1;
+        W.flag[lane] = 0;
         if (b < sb.B) {
             const double* sd = sb.seed + b * sb.seed_stride;
-            Goal goal;
-            goal_from_pose(sb.goal_pose + 7 * b, goal);
-            store_goal(L.goal + 7 * tid, goal);
-            const ConfigView cv = plain_view(sd, 1);
-            Frame F;
-            fk_full(rb, cv, F, nullptr);
-            const double c = total_cost(rb, pr, goal, F, cv, sd);
+            double* g7 = W.goal + 7 * lane;
+            goal_from_pose(sb.goal_pose + 7 * b, g7);
+            double* col = W.q + lane;
             double* hdr = sb.hdr + (size_t)b * (n + 2);
-            for (int j = 0; j < n; ++j) hdr[j] = sd[j];  // best_ = {seed, cost(seed)}, ik_memetic.cpp:18-22
+            for (int j = 0; j < n; ++j) {
+                col[j * kS] = sd[j];
+                hdr[j] = sd[j];  // best_ = {seed, cost(seed)}, ik_memetic.cpp:18-22
+            }
+            double aux[5];
+            const double c = eval_chain(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
             hdr[n] = c;
             hdr[n + 1] = 0.0;
             ProblemMeta m{0, 0, kActive, 0};
-            const bool s = solution_test(rb, pr, goal, F, cv, sd);
+            const bool s = solution_from_aux(aux);
             bool done = false, found = false;
-            if (pr.stop_on_valid && s) {  // ik_memetic.cpp:294-296
+            if (c_pr.stop_on_valid && s) {  // ik_memetic.cpp:294-296
                 done = found = true;
-            } else if (pr.max_generations <= 0) {
+            } else if (c_pr.max_generations <= 0) {
                 done = true;
-                found = (!pr.stop_on_valid && s) || pr.approx;
+                found = (!c_pr.stop_on_valid && s) || c_pr.approx;
             }
             if (done) {
                 m.status = found ? kSolved : kFailed;
@@ -309,278 +299,405 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
                     atomicAdd(&sb.stats[3], 1ull);
                 }
             } else {
-                L.flag[tid] = 1;
-                const int pos = atomicAdd(&sb.counters[0], 1);
-                sb.active[pos] = (int32_t)b;
+                W.flag[lane] = 1;
+                keep = true;
             }
             sb.meta[b] = m;
         }
     }
-    __syncthreads();
-    init_population_coop(rb, pr, sb, L, T, G, tid);
+    {
+        const unsigned mask = __ballot_sync(kFull, keep);
+        int basepos = 0;
+        if (lane == 0 && mask) basepos = atomicAdd(&sb.counters[0], __popc(mask));
+        basepos = __shfl_sync(kFull, basepos, 0);
+        if (keep) sb.active[basepos + __popc(mask & ((1u << lane) - 1u))] = (int32_t)b;
+    }
+    __syncwarp();
+    init_population_warp(sb, W, PW, lane);
 }
 
 // -----------------------------------------------------------------------------------------------
-// One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for G problems per CTA.
+// gradientDescent(i) (src/ik_memetic.cpp:66-91) with L lanes per elite: the 2n finite-difference
+// evaluations of a step run on different lanes (each a full chain walk with the cached sin/cos of the
+// unperturbed joints), the two line-search points on two lanes, the accepted point on the group leader.
+// Column c holds the GD state of group c.  Returns the number of step() executions of this lane's group.
 // -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) memetic_generation_kernel(const __grid_constant__ DevRobot rb,
-                                                                      const __grid_constant__ DevParams pr,
-                                                                      const __grid_constant__ SolveBuffers sb,
-                                                                      int list_in, int G) {
+__device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane, bool valid, const double* g7,
+                                             const double* sd, double& best_cost_out) {
+    const int n = c_rb.n;
+    const int c = lane / L, gl = lane % L;
+    const bool leader = gl == 0;
+    double* q = W.q + c;
+    double* g = W.g + c;
+    double* best = W.best + c;
+    double* sc = W.sc + c;
+    const double h = c_pr.step_size;
+    double local_cost = 0.0, best_cost = 0.0, previous_cost = 0.0;
+    int it = 0;
+    if (valid && leader) local_cost = best_cost = eval_chain(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
+    bool act_l = valid && leader && c_pr.gd_max_iters > 0;
+    int steps = 0;
+    __syncwarp();
+    for (;;) {
+        const bool act = __shfl_sync(kFull, act_l ? 1 : 0, c * L) != 0 && valid;
+        if (!__any_sync(kFull, act)) break;
+        for (int r = 0; r * L < 2 * n; ++r) {
+            const int k = r * L + gl;
+            if (act && k < 2 * n) {
+                const int i = k >> 1;
+                const double qi = q[i * kS];
+                W.cs[k * 16 + c] = eval_chain(q, nullptr, kViewFd, i, (k & 1) ? qi + h : qi - h, sc, nullptr, g7, sd, nullptr);
+            }
+        }
+        __syncwarp();
+        if (act && leader) {
+            double sum = h;
+            for (int i = 0; i < n; ++i) {
+                const double gi = W.cs[(2 * i + 1) * 16 + c] - W.cs[(2 * i) * 16 + c];
+                g[i * kS] = gi;
+                sum = sum + fabs(gi);
+            }
+            normalise_gradient(g, sum);
+        }
+        __syncwarp();
+        if (act && gl < 2 && gl < L)
+            W.cs[gl * 16 + c] = eval_chain(q, g, gl == 0 ? kViewMinus : kViewPlus, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
+        __syncwarp();
+        if (act && leader) {
+            accept_step(q, g, W.cs[c], W.cs[16 + c]);
+            local_cost = eval_chain(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
+            if (local_cost < best_cost) {
+                for (int j = 0; j < n; ++j) best[j * kS] = q[j * kS];
+                best_cost = local_cost;
+            }
+            ++steps;
+            if (fabs(local_cost - previous_cost) <= c_pr.min_cost_delta) {
+                act_l = false;
+            } else {
+                previous_cost = local_cost;
+                ++it;
+                if (it >= c_pr.gd_max_iters) act_l = false;
+            }
+        }
+        __syncwarp();
+    }
+    best_cost_out = best_cost;
+    return steps;
+}
+
+// -----------------------------------------------------------------------------------------------
+// One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for PW problems per warp.
+// -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
+                                                                      int list_in, int L, int PW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = rb.n, P = pr.P, E = pr.E;
-    const int F2 = 2 * n + 2;
-    const int T = kThreads;
-    const int tid = threadIdx.x;
+    const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_active = sb.counters[list_in];
-    const int64_t base = (int64_t)blockIdx.x * G;
+    const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * PW;
     if (base >= n_active) return;
-    const MemSmem L = carve(smem_raw, n, P, E, T, G);
+    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P), n, P);
     const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;
     int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
 
-    if (tid < G) {
-        const int64_t idx = base + tid;
+    if (lane < PW) {
+        const int64_t idx = base + lane;
         const int b = idx < n_active ? act_in[idx] : -1;
-        L.pidx[tid] = b;
-        L.flag[tid] = 0;
-        L.pool_size[tid] = E;
-        L.start[tid] = b >= 0 ? E : P;
-        L.first_rem[tid] = INT_MAX;
-        for (int e = 0; e < E; ++e) L.pool[tid * E + e] = e;
-        if (b >= 0) {
-            Goal goal;
-            goal_from_pose(sb.goal_pose + 7 * (size_t)b, goal);
-            store_goal(L.goal + 7 * tid, goal);
-        }
+        W.pidx[lane] = b;
+        W.flag[lane] = 0;
+        if (b >= 0) goal_from_pose(sb.goal_pose + 7 * (size_t)b, W.goal + 7 * lane);
     }
-    if (tid == 0) L.misc[0] = 0;
-    __syncthreads();
-    for (int item = tid; item < G * P; item += T) {
-        const int b = L.pidx[item / P];
-        L.ord[item] = b >= 0 ? sb.order[(size_t)b * P + (item % P)] : (uint16_t)0;
-    }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- gradientDescent(i) for every elite (src/ik_memetic.cpp:66-91, 230-239): one GD instance per thread
+    // ---- gradientDescent(i) for every elite (src/ik_memetic.cpp:66-91, 230-239)
+    int gd_steps = 0;
     {
-        const int p = tid / E, e = tid % E;
-        const int b = tid < G * E ? L.pidx[p] : -1;
-        if (b >= 0) {
+        const int c = lane / L;            // GD column = elite group
+        const int k = c / E, e = c % E;    // problem slot, elite
+        const int b = c < PW * E ? W.pidx[k] : -1;
+        const bool valid = b >= 0;
+        const bool leader = (lane % L) == 0;
+        const double* sd = nullptr;
+        const double* src = nullptr;
+        double* dst = nullptr;
+        int slot = 0;
+        if (valid) {
             const int iter = sb.meta[b].iter;
-            const int slot = L.ord[p * P + e];
-            const double* src = pop_ptr(sb, iter & 1, b, n, P);
-            double* dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
-            const double* sd = sb.seed + (size_t)b * sb.seed_stride;
-            GdState st{L.uni + tid, L.uni + (size_t)n * T + tid, L.uni + 2 * (size_t)n * T + tid,
-                       L.uni + 3 * (size_t)n * T + tid, T, 0.0, 0.0};
-            for (int j = 0; j < n; ++j) {
-                const double v = src[(size_t)j * P + slot];
-                st.q[j * T] = v;
-                st.best[j * T] = v;
-                st.g[j * T] = 0.0;
-            }
-            Goal goal;
-            load_goal(L.goal + 7 * p, goal);
-            st.local_cost = st.best_cost = cost_full(rb, pr, goal, plain_view(st.q, T), sd, st.sc);
-            int it = 0;
-            double previous_cost = 0.0;
-            while (it < pr.gd_max_iters) {
-                Frame FL;
-                gd_step(rb, pr, goal, st, sd, FL);
-                if (fabs(st.local_cost - previous_cost) <= pr.min_cost_delta) {
-                    ++it;
-                    break;
+            slot = order_ptr(sb, iter & 1, b, P)[e];
+            src = pop_ptr(sb, iter & 1, b, n, P);
+            dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
+            sd = sb.seed + (size_t)b * sb.seed_stride;
+            if (leader) {
+                for (int j = 0; j < n; ++j) {
+                    const double v = src[(size_t)j * P + slot];
+                    W.q[j * kS + c] = v;
+                    W.best[j * kS + c] = v;
+                    W.g[j * kS + c] = 0.0;  // GradientIk::from: zero gradient
                 }
-                previous_cost = st.local_cost;
-                ++it;
             }
-            atomicAdd(&L.misc[0], it);  // GD step() executions (`it` counts the breaking step as well)
-            // genes <- best, fitness <- cost_fn(best) (== best_cost: same genes, deterministic cost),
-            // gradient <- the last normalised gradient (ik_memetic.cpp:88-90)
-            double* row = L.el + (size_t)(p * E + e) * F2;
+        }
+        __syncwarp();
+        double best_cost = 0.0;
+        if (L == 1) {
+            if (valid) {
+                GdState st{W.q + c, W.g + c, W.best + c, W.sc + c, 0.0, 0.0};
+                const double* g7 = W.goal + 7 * k;
+                st.local_cost = st.best_cost = eval_chain(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, nullptr);
+                int it = 0;
+                double previous_cost = 0.0;
+                while (it < c_pr.gd_max_iters) {
+                    gd_step(st, g7, sd, nullptr);
+                    ++gd_steps;
+                    if (fabs(st.local_cost - previous_cost) <= c_pr.min_cost_delta) break;
+                    previous_cost = st.local_cost;
+                    ++it;
+                }
+                best_cost = st.best_cost;
+            }
+        } else {
+            const int steps = gd_elite_wide(W, L, lane, valid, W.goal + 7 * (valid ? k : 0), sd, best_cost);
+            if (leader) gd_steps = steps;
+        }
+        // genes <- best, fitness <- cost_fn(best) (== best_cost: same genes, deterministic cost),
+        // gradient <- the last normalised gradient (ik_memetic.cpp:88-90)
+        if (valid && leader) {
             for (int j = 0; j < n; ++j) {
-                const double gj = st.g[j * T], bj = st.best[j * T];
-                row[j] = bj;
-                row[n + j] = gj;
-                dst[(size_t)j * P + slot] = bj;
-                dst[(size_t)(n + j) * P + slot] = gj;
+                dst[(size_t)j * P + slot] = W.best[j * kS + c];
+                dst[(size_t)(n + j) * P + slot] = W.g[j * kS + c];
             }
             const double ext = src[(size_t)(2 * n + 1) * P + slot];
-            row[2 * n] = st.best_cost;
-            row[2 * n + 1] = ext;
-            dst[(size_t)(2 * n) * P + slot] = st.best_cost;
+            W.efit[c] = best_cost;
+            W.eext[c] = ext;
+            dst[(size_t)(2 * n) * P + slot] = best_cost;
             dst[(size_t)(2 * n + 1) * P + slot] = ext;
         }
     }
-    __syncthreads();
-    if (tid < G * E && L.pidx[tid / E] >= 0) L.fit[(tid / E) * P + (tid % E)] = L.el[(size_t)tid * F2 + 2 * n];
-    __syncthreads();
+    __syncwarp();
 
-    // ---- reproduce (src/ik_memetic.cpp:119-190).  The reference walks the children in order and a child
-    // that beats a parent removes it from the mating pool, which changes the parent draws of every later
-    // child.  Here all uncommitted children are produced against the current pool; the lowest child that
-    // removes a parent is found; children up to it are committed, the pool shrinks and the rest are
-    // produced again.  Each child's random stream is keyed by (generation, child), so its draws do not
-    // depend on the history.  At most E + 1 rounds.
-    {
-        const int C = P - E;
-        const double inv_n = 1.0 / (double)n;
-        double* col = L.cg + tid;
-        for (;;) {
-            for (int item = tid; item < G * C; item += T) {
-                const int p = item / C, i = E + item % C;
-                if (i < L.start[p]) continue;
-                const int b = L.pidx[p];
-                const int iter = sb.meta[b].iter;
-                const int slot = L.ord[p * P + i];
-                double* dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
-                const double* sd = sb.seed + (size_t)b * sb.seed_stride;
-                Goal goal;
-                load_goal(L.goal + 7 * p, goal);
-                Rng rng;
-                rng_init(rng, pr.seed_lo, pr.seed_hi, (uint32_t)(sb.first_problem_index + b), kStreamReproduce,
-                         (uint32_t)iter, (uint32_t)i);
-                const int ps = L.pool_size[p];
-                double f;
+    // ---- per problem: reproduce, sortPopulation, best update
+    const double inv_n = 1.0 / (double)n;
+    int n_problems = 0;
+    for (int k = 0; k < PW; ++k) {
+        const int b = W.pidx[k];
+        if (b < 0) continue;
+        ++n_problems;
+        const int iter = sb.meta[b].iter;
+        const double* src = pop_ptr(sb, iter & 1, b, n, P);
+        double* dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
+        const uint16_t* ord_in = order_ptr(sb, iter & 1, b, P);
+        uint16_t* ord_out = order_ptr(sb, (iter & 1) ^ 1, b, P);
+        const double* sd = sb.seed + (size_t)b * sb.seed_stride;
+        const double* g7 = W.goal + 7 * k;
+        const int c0 = k * E;  // first elite column of this problem
+        if (lane < E) {
+            W.fit[lane] = W.efit[c0 + lane];
+            W.pool[lane] = lane;
+        }
+        if (lane == 0) W.ctl[0] = E;
+        __syncwarp();
+
+        // reproduce (src/ik_memetic.cpp:119-190).  A child that beats a parent removes it from the mating
+        // pool, which changes the parent draws of every later child: a window is committed up to the first
+        // such child and the walk resumes after it.  Each child's random stream is keyed by (generation,
+        // child), so its draws do not depend on the history.
+        int s = E;
+        double* col = W.q + lane;
+        while (s < P) {
+            const int i = s + lane;
+            const bool actv = i < P;
+            const int ps = W.ctl[0];
+            double f = 0.0;
+            int ia = 0, ib = 0;
+            bool removes = false;
+            if (actv) {
+                const int slot = ord_in[i];
                 if (ps > 0) {
-                    const uint32_t idxA = rng_uniform_int(rng, (uint32_t)ps);
+                    const Stream st = make_stream((uint32_t)(sb.first_problem_index + b), kStreamReproduce,
+                                                  (uint32_t)iter, (uint32_t)i);
+                    uint32_t m0, m1, m2, m3;
+                    IndexWords iw;
+                    iw.st = st;
+                    philox_block(st, 0, iw.h0, iw.h1, iw.h2, iw.h3);
+                    philox_block(st, 1, m0, m1, m2, m3);
+                    iw.h4 = m2;
+                    iw.h5 = m3;
+                    iw.v0 = iw.v1 = iw.v2 = iw.v3 = 0;
+                    iw.ovf_block = (uint32_t)(2 * n + 2);
+                    iw.pos = 0;
+                    const uint32_t idxA = uniform_int_words(iw, (uint32_t)ps);
                     uint32_t idxB = idxA;
-                    while (idxB == idxA && ps > 1) idxB = rng_uniform_int(rng, (uint32_t)ps);
-                    const int ia = L.pool[p * E + idxA], ib = L.pool[p * E + idxB];
-                    const double* A = L.el + (size_t)(p * E + ia) * F2;
-                    const double* Bp = L.el + (size_t)(p * E + ib) * F2;
-                    const double extinction = 0.5 * (A[2 * n + 1] + Bp[2 * n + 1]);
+                    while (idxB == idxA && ps > 1) idxB = uniform_int_words(iw, (uint32_t)ps);
+                    ia = W.pool[idxA];
+                    ib = W.pool[idxB];
+                    const int ca = c0 + ia, cb = c0 + ib;
+                    const double extinction = 0.5 * (W.eext[ca] + W.eext[cb]);
                     const double mutation_prob = extinction * (1.0 - inv_n) + inv_n;
-                    const double mix = rng_uniform_real(rng, 0.0, 1.0);
+                    const double mix = uniform_real_words(0.0, 1.0, m0, m1);
+#pragma unroll 1
                     for (int j = 0; j < n; ++j) {
-                        double gene = mix * A[j] + (1.0 - mix) * Bp[j];
-                        const double rA = rng_uniform_real(rng, 0.0, 1.0);
-                        const double rB = rng_uniform_real(rng, 0.0, 1.0);
-                        gene = gene + (rA * A[n + j] + rB * Bp[n + j]);
+                        uint32_t a0, a1, a2, a3, u0, u1, u2, u3;
+                        philox_block(st, (uint32_t)(2 + 2 * j), a0, a1, a2, a3);
+                        philox_block(st, (uint32_t)(3 + 2 * j), u0, u1, u2, u3);
+                        double gene = mix * W.best[j * kS + ca] + (1.0 - mix) * W.best[j * kS + cb];
+                        const double rA = uniform_real_words(0.0, 1.0, a0, a1);
+                        const double rB = uniform_real_words(0.0, 1.0, a2, a3);
+                        gene = gene + (rA * W.g[j * kS + ca] + rB * W.g[j * kS + cb]);
                         const double original = gene;
-                        if (rng_uniform_real(rng, 0.0, 1.0) < mutation_prob)
-                            gene = gene + extinction * rb.vhalf[j] * rng_uniform_real(rng, -1.0, 1.0);
-                        gene = clamp_to_limits(rb, j, gene);
-                        col[j * T] = gene;
+                        if (uniform_real_words(0.0, 1.0, u0, u1) < mutation_prob)
+                            gene = gene + extinction * c_rb.vhalf[j] * uniform_real_words(-1.0, 1.0, u2, u3);
+                        gene = clamp_to_limits(j, gene);
+                        col[j * kS] = gene;
                         dst[(size_t)j * P + slot] = gene;
                         dst[(size_t)(n + j) * P + slot] = gene - original;
                     }
-                    f = cost_full(rb, pr, goal, plain_view(col, T), sd, nullptr);
-                    L.par[2 * (p * P + i)] = (uint8_t)ia;
-                    L.par[2 * (p * P + i) + 1] = (uint8_t)ib;
-                    if (f < A[2 * n] || f < Bp[2 * n]) atomicMin(&L.first_rem[p], i);
                 } else {
                     // empty pool: a random individual seeded from the slot's previous occupant
-                    const double* src = pop_ptr(sb, iter & 1, b, n, P);
-                    for (int j = 0; j < n; ++j) col[j * T] = src[(size_t)j * P + slot];
-                    random_valid_configuration(rb, rng, col, T);
-                    f = cost_full(rb, pr, goal, plain_view(col, T), sd, nullptr);
+                    const Stream st = make_stream((uint32_t)(sb.first_problem_index + b), kStreamRandomChild,
+                                                  (uint32_t)iter, (uint32_t)i);
+                    for (int j = 0; j < n; ++j) col[j * kS] = src[(size_t)j * P + slot];
+                    random_valid_configuration(st, col);
                     for (int j = 0; j < n; ++j) {
-                        dst[(size_t)j * P + slot] = col[j * T];
+                        dst[(size_t)j * P + slot] = col[j * kS];
                         dst[(size_t)(n + j) * P + slot] = 0.0;
                     }
                 }
+                f = eval_chain(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
                 dst[(size_t)(2 * n) * P + slot] = f;
-                L.fit[p * P + i] = f;
+                if (ps > 0) removes = f < W.efit[c0 + ia] || f < W.efit[c0 + ib];
             }
-            __syncthreads();
-            int pending = 0;
-            if (tid < G && L.start[tid] < P) {
-                const int p = tid;
-                const int istar = L.first_rem[p];
-                if (istar < P) {
-                    const double f = L.fit[p * P + istar];
-                    const int ia = L.par[2 * (p * P + istar)], ib = L.par[2 * (p * P + istar) + 1];
-                    int ps = L.pool_size[p];
+            const unsigned mask = __ballot_sync(kFull, removes);
+            if (mask) {
+                const int l = __ffs(mask) - 1;
+                const double fl = __shfl_sync(kFull, f, l);
+                const int a = __shfl_sync(kFull, ia, l), bb = __shfl_sync(kFull, ib, l);
+                if (actv && lane <= l) W.fit[i] = f;
+                if (lane == 0) {
+                    int p2 = ps;
                     // parents are referenced by identity; A first, then B (ik_memetic.cpp:170-177)
                     for (int which = 0; which < 2; ++which) {
-                        const int target = which == 0 ? ia : ib;
-                        if (f < L.el[(size_t)(p * E + target) * F2 + 2 * n]) {
-                            for (int k = 0; k < ps; ++k)
-                                if (L.pool[p * E + k] == target) {
-                                    for (int l = k; l + 1 < ps; ++l) L.pool[p * E + l] = L.pool[p * E + l + 1];
-                                    --ps;
+                        const int target = which == 0 ? a : bb;
+                        if (fl < W.efit[c0 + target]) {
+                            for (int x = 0; x < p2; ++x)
+                                if (W.pool[x] == target) {
+                                    for (int y = x; y + 1 < p2; ++y) W.pool[y] = W.pool[y + 1];
+                                    --p2;
                                     break;
                                 }
                         }
                     }
-                    L.pool_size[p] = ps;
-                    L.start[p] = istar + 1;
-                    L.first_rem[p] = INT_MAX;
-                } else {
-                    L.start[p] = P;
+                    W.ctl[0] = p2;
                 }
-                pending = L.start[p] < P;
+                s += l + 1;
+            } else {
+                if (actv) W.fit[i] = f;
+                s += 32;
             }
-            if (!__syncthreads_or(pending)) break;
+            __syncwarp();
         }
+
+        // sortPopulation (src/ik_memetic.cpp:200-209) under the total order (fitness, position), NaN last.
+        if (c_rb.any_unbounded) {
+            // whole order needed: the previous occupant of every position may seed a random individual
+            for (int i = lane; i < P; i += 32) {
+                const double fi = W.fit[i];
+                int rank = 0;
+                for (int j = 0; j < P; ++j) rank += key_less(W.fit[j], j, fi, i) ? 1 : 0;
+                ord_out[rank] = ord_in[i];
+                if (rank < E) W.top[rank] = i;
+                if (rank == P - 1) W.top[E] = i;
+            }
+            __syncwarp();
+        } else {
+            // only the E best (the next parents) and the worst (extinction scale) matter: E + 1 warp reductions
+            for (int i = lane; i < P; i += 32) ord_out[i] = ord_in[i];
+            double pf = -INFINITY;
+            int pi = -1;
+            for (int r = 0; r <= E; ++r) {
+                const bool want_max = r == E;
+                double mf = want_max ? -INFINITY : make_nan();
+                int mi = want_max ? -1 : INT_MAX;
+                for (int i = lane; i < P; i += 32) {
+                    const double fi = W.fit[i];
+                    if (want_max) {
+                        if (key_less(mf, mi, fi, i)) { mf = fi; mi = i; }
+                    } else if (key_less(pf, pi, fi, i) && key_less(fi, i, mf, mi)) {
+                        mf = fi; mi = i;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double of = __shfl_xor_sync(kFull, mf, o);
+                    const int oi = __shfl_xor_sync(kFull, mi, o);
+                    const bool take = want_max ? key_less(mf, mi, of, oi) : key_less(of, oi, mf, mi);
+                    if (take) { mf = of; mi = oi; }
+                }
+                if (lane == 0) W.top[r] = mi;
+                pf = mf;
+                pi = mi;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // bring the E best to the front of the slot-index row with swaps
+                for (int r = 0; r < E; ++r) W.pool[r] = W.top[r];
+                for (int r = 0; r < E; ++r) {
+                    const int at = W.pool[r];
+                    if (at != r) {
+                        const uint16_t tmp = ord_out[r];
+                        ord_out[r] = ord_out[at];
+                        ord_out[at] = tmp;
+                        for (int r2 = r + 1; r2 < E; ++r2)
+                            if (W.pool[r2] == r) W.pool[r2] = at;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // computeExtinctions (ik_memetic.cpp:57-64); only the next generation's parents are ever read
+        const double f0 = W.fit[W.top[0]];
+        const double fmax = W.fit[W.top[E]];
+        if (lane < E) {
+            const double grading = (double)lane / (double)(P - 1);
+            dst[(size_t)(2 * n + 1) * P + ord_out[lane]] = (W.fit[W.top[lane]] + f0 * (grading - 1.0)) / fmax;
+        }
+        double* hdr = sb.hdr + (size_t)b * (n + 2);
+        if (f0 < hdr[n]) {  // best_ = best_curr_, ik_memetic.cpp:206-208
+            const int slot0 = ord_out[0];
+            __syncwarp();
+            if (lane < n) hdr[lane] = dst[(size_t)lane * P + slot0];
+            if (lane == 0) hdr[n] = f0;
+        }
+        if (lane == 0) W.f0s[k] = f0;
+        __syncwarp();
     }
 
-    // ---- sortPopulation (src/ik_memetic.cpp:200-209): rank of every position under (fitness, position),
-    // NaN last; the new order row is scattered straight to global memory.
-    for (int item = tid; item < G * P; item += T) {
-        const int p = item / P, i = item % P;
-        const int b = L.pidx[p];
-        if (b < 0) continue;
-        const double* fp = L.fit + p * P;
-        const double fi = fp[i];
-        int rank = 0;
-        for (int j = 0; j < P; ++j) {
-            const double fj = fp[j];
-            const bool lji = fit_less(fj, fi), lij = fit_less(fi, fj);
-            rank += (lji || (!lij && j < i)) ? 1 : 0;
-        }
-        sb.order[(size_t)b * P + rank] = L.ord[p * P + i];
-        if (rank < E) L.top[p * (E + 1) + rank] = i;
-        if (rank == P - 1) L.top[p * (E + 1) + E] = i;
-    }
-    __syncthreads();
-
-    // ---- per problem: extinctions, best update, solution test, wipeout check, bookkeeping
+    // ---- per problem, one lane each: solution test, wipeout check, bookkeeping
     {
         bool keep = false;
         int b = -1;
-        if (tid < G && L.pidx[tid] >= 0) {
-            const int p = tid;
-            b = L.pidx[p];
+        if (lane < PW && W.pidx[lane] >= 0) {
+            const int k = lane;
+            b = W.pidx[k];
             ProblemMeta m = sb.meta[b];
             const int iter = m.iter;
-            double* dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
             const double* sd = sb.seed + (size_t)b * sb.seed_stride;
-            const int* top = L.top + p * (E + 1);
-            const double* fp = L.fit + p * P;
-            const double f0 = fp[top[0]];
-            const double fmax = fp[top[E]];
-            // computeExtinctions (ik_memetic.cpp:57-64); only the next generation's parents are ever read
-            for (int r = 0; r < E; ++r) {
-                const int ir = top[r];
-                const double grading = (double)r / (double)(P - 1);
-                dst[(size_t)(2 * n + 1) * P + L.ord[p * P + ir]] = (fp[ir] + f0 * (grading - 1.0)) / fmax;
-            }
             double* hdr = sb.hdr + (size_t)b * (n + 2);
-            if (f0 < hdr[n]) {  // best_ = best_curr_, ik_memetic.cpp:206-208
-                const int slot0 = L.ord[p * P + top[0]];
-                for (int j = 0; j < n; ++j) hdr[j] = dst[(size_t)j * P + slot0];
-                hdr[n] = f0;
-            }
-            const bool final_gen = iter + 1 >= pr.max_generations;
+            const double f0 = W.f0s[k];
+            const bool final_gen = iter + 1 >= c_pr.max_generations;
             bool s = false;
-            if (pr.stop_on_valid || final_gen) {
-                Goal goal;
-                load_goal(L.goal + 7 * p, goal);
-                const ConfigView cv = plain_view(hdr, 1);
-                Frame FB;
-                fk_full(rb, cv, FB, nullptr);
-                s = solution_test(rb, pr, goal, FB, cv, sd);
+            if (c_pr.stop_on_valid || final_gen) {
+                double* col = W.q + lane;
+                for (int j = 0; j < n; ++j) col[j * kS] = hdr[j];
+                double aux[5];
+                eval_chain(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k, sd, aux);
+                s = solution_from_aux(aux);
             }
             bool done = false, found = false;
             int its = iter;
-            if (pr.stop_on_valid && s) {  // ik_memetic.cpp:252-255
+            if (c_pr.stop_on_valid && s) {  // ik_memetic.cpp:252-255
                 done = found = true;
             } else if (final_gen) {  // ik_memetic.cpp:272-282
                 done = true;
-                found = (!pr.stop_on_valid && s) || pr.approx;
+                found = (!c_pr.stop_on_valid && s) || c_pr.approx;
                 its = iter + 1;
             }
             if (done) {
@@ -594,33 +711,34 @@ __global__ void __launch_bounds__(kThreads) memetic_generation_kernel(const __gr
             } else {
                 // checkWipeout (ik_memetic.cpp:43-55)
                 bool wipe = false;
-                if (m.has_prev) wipe = !(f0 < hdr[n + 1] - pr.wipeout_tol);
+                if (m.has_prev) wipe = !(f0 < hdr[n + 1] - c_pr.wipeout_tol);
                 if (!wipe) {
                     m.has_prev = 1;
                     hdr[n + 1] = f0;
                 }
-                L.flag[p] = wipe ? 1 : 0;
+                W.flag[k] = wipe ? 1 : 0;
                 m.iter = iter + 1;
                 keep = true;
             }
             sb.meta[b] = m;
         }
-        if (tid < 32) {  // G <= 32: the bookkeeping threads are warp 0
-            const unsigned mask = __ballot_sync(0xffffffffu, keep);
-            int basepos = 0;
-            if ((tid & 31) == 0 && mask) basepos = atomicAdd(&sb.counters[list_in ^ 1], __popc(mask));
-            basepos = __shfl_sync(0xffffffffu, basepos, 0);
-            if (keep) act_out[basepos + __popc(mask & ((1u << tid) - 1u))] = b;
-            if (tid == 0 && sb.stats) {
-                int cnt = 0;
-                for (int p = 0; p < G; ++p) cnt += L.pidx[p] >= 0 ? 1 : 0;
-                atomicAdd(&sb.stats[0], (unsigned long long)cnt);
-                atomicAdd(&sb.stats[1], (unsigned long long)L.misc[0]);
+        const unsigned mask = __ballot_sync(kFull, keep);
+        int basepos = 0;
+        if (lane == 0 && mask) basepos = atomicAdd(&sb.counters[list_in ^ 1], __popc(mask));
+        basepos = __shfl_sync(kFull, basepos, 0);
+        if (keep) act_out[basepos + __popc(mask & ((1u << lane) - 1u))] = b;
+        if (sb.stats) {
+            int steps = gd_steps;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(kFull, steps, o);
+            if (lane == 0) {
+                atomicAdd(&sb.stats[0], (unsigned long long)n_problems);
+                atomicAdd(&sb.stats[1], (unsigned long long)steps);
             }
         }
     }
-    __syncthreads();
-    init_population_coop(rb, pr, sb, L, T, G, tid);
+    __syncwarp();
+    init_population_warp(sb, W, PW, lane);
 }
 
 __global__ void fp64_peak_kernel(double* sink, int iters) {
@@ -637,62 +755,75 @@ __global__ void fp64_peak_kernel(double* sink, int iters) {
 
 }  // namespace
 
-MemeticShape memetic_shape(int n, int P, int E) {
+int memetic_max_lanes_per_elite(int E) {
+    int L = 32 / E;
+    if (L > 16) L = 16;
+    return L < 1 ? 1 : L;
+}
+
+MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
     MemeticShape s;
     s.threads = kThreads;
-    int G = kThreads / E;
-    if (G > 32) G = 32;
-    if (G < 1) G = 1;
-    size_t off[13];
-    // keep at least three CTAs per SM where the population allows it
-    while (G > 1 && memetic_smem_layout(n, P, E, kThreads, G, off) > 74 * 1024) G >>= 1;
-    s.group = G;
-    s.smem = memetic_smem_layout(n, P, E, kThreads, G, off);
+    s.warps = kWarpsPerBlock;
+    int L = lanes_per_elite < 1 ? 1 : lanes_per_elite;
+    if (L > memetic_max_lanes_per_elite(E)) L = memetic_max_lanes_per_elite(E);
+    s.lanes_per_elite = L;
+    s.problems_per_warp = 32 / (E * L);
+    s.smem = kWarpsPerBlock * warp_smem_bytes(n, P);
     return s;
 }
 
-size_t gd_local_smem_bytes(int n, int threads) { return 5 * (size_t)n * threads * sizeof(double); }
+size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 7) * kS * sizeof(double); }
 
 cudaError_t configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(memetic_generation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(memetic_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(eval_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(gd_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-cudaError_t launch_eval_cost(cudaStream_t stream, const DevRobot& robot, const DevParams& pr, int64_t B,
-                             const double* goal_pose, const double* seed, int64_t seed_stride, const double* q,
-                             double* cost, int32_t* is_solution, double* tip_pose) {
+cudaError_t upload_constants(cudaStream_t stream, const DevRobot& robot, const DevParams& pr) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_rb, &robot, sizeof(DevRobot), 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(c_pr, &pr, sizeof(DevParams), 0, cudaMemcpyHostToDevice, stream);
+}
+
+cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double* goal_pose, const double* seed,
+                             int64_t seed_stride, const double* q, double* cost, int32_t* is_solution,
+                             double* tip_pose) {
     if (B <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((B + kThreads - 1) / kThreads);
-    eval_cost_kernel<<<blocks, kThreads, 0, stream>>>(robot, pr, B, goal_pose, seed, seed_stride, q, cost, is_solution,
-                                                     tip_pose);
+    const size_t smem = (size_t)kWarpsPerBlock * (n + 7) * kS * sizeof(double);
+    eval_cost_kernel<<<blocks, kThreads, smem, stream>>>(B, goal_pose, seed, seed_stride, q, cost, is_solution, tip_pose);
     return cudaGetLastError();
 }
 
-cudaError_t launch_gd_local(cudaStream_t stream, const DevRobot& robot, const DevParams& pr, const SolveBuffers& sb) {
+cudaError_t launch_gd_local(cudaStream_t stream, int n, const SolveBuffers& sb) {
     if (sb.B <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((sb.B + kThreads - 1) / kThreads);
-    gd_local_kernel<<<blocks, kThreads, gd_local_smem_bytes(robot.n, kThreads), stream>>>(robot, pr, sb);
+    gd_local_kernel<<<blocks, kThreads, gd_local_smem_bytes(n), stream>>>(sb);
     return cudaGetLastError();
 }
 
-cudaError_t launch_memetic_init(cudaStream_t stream, const DevRobot& robot, const DevParams& pr,
-                                const SolveBuffers& sb) {
+cudaError_t launch_memetic_init(cudaStream_t stream, int n, int P, int E, const SolveBuffers& sb) {
     if (sb.B <= 0) return cudaSuccess;
-    const MemeticShape s = memetic_shape(robot.n, pr.P, pr.E);
-    const unsigned blocks = (unsigned)((sb.B + s.group - 1) / s.group);
-    memetic_init_kernel<<<blocks, s.threads, s.smem, stream>>>(robot, pr, sb, s.group);
+    const MemeticShape s = memetic_shape(n, P, E, 1);
+    const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
+    const unsigned blocks = (unsigned)((sb.B + per_block - 1) / per_block);
+    memetic_init_kernel<<<blocks, s.threads, s.smem, stream>>>(sb, s.problems_per_warp);
     return cudaGetLastError();
 }
 
-cudaError_t launch_memetic_generation(cudaStream_t stream, const DevRobot& robot, const DevParams& pr,
-                                      const SolveBuffers& sb, int list_in, int64_t n_active) {
+cudaError_t launch_memetic_generation(cudaStream_t stream, int n, int P, int E, const SolveBuffers& sb, int list_in,
+                                      int64_t n_active, int lanes_per_elite) {
     if (n_active <= 0) return cudaSuccess;
-    const MemeticShape s = memetic_shape(robot.n, pr.P, pr.E);
-    const unsigned blocks = (unsigned)((n_active + s.group - 1) / s.group);
-    memetic_generation_kernel<<<blocks, s.threads, s.smem, stream>>>(robot, pr, sb, list_in, s.group);
+    const MemeticShape s = memetic_shape(n, P, E, lanes_per_elite);
+    const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
+    const unsigned blocks = (unsigned)((n_active + per_block - 1) / per_block);
+    memetic_generation_kernel<<<blocks, s.threads, s.smem, stream>>>(sb, list_in, s.lanes_per_elite, s.problems_per_warp);
     return cudaGetLastError();
 }
 
