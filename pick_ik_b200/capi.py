@@ -14,7 +14,7 @@ import numpy as np
 from .robots import JOINT_DESC_DTYPE, RobotChain
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpik_b200.so")
+LIB_PATH = os.environ.get("PIK_LIB_PATH") or os.path.join(HERE, "libpik_b200.so")  # override: A/B experiments only
 
 PIK_OK = 0
 PIK_SUCCESS = 1

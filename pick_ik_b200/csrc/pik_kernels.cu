@@ -29,6 +29,10 @@ namespace pik {
 
 namespace {
 
+#ifndef PIK_GEN_MIN_BLOCKS
+#define PIK_GEN_MIN_BLOCKS 4
+#endif
+
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = 32 * kWarpsPerBlock;
 constexpr unsigned kFull = 0xffffffffu;
@@ -39,9 +43,10 @@ struct WarpSmem {
     double* g;
     double* best;
     double* sc;
-    double* cs;    // [2n][16] finite-difference / line-search costs of the lane-parallel GD step
+    double* cs;    // [2n][16] finite-difference / line-search costs of the lane-parallel GD step: columns 16..31 of
+                   // the sc rows, which a lane-parallel step (at most 16 elite groups per warp) never uses
     double* fit;   // [P] fitness by population position of the problem being reproduced / sorted
-    double* goal;  // [32][7]
+    double* goal;  // [PW][7]
     double* efit;  // [32] elite fitness by column
     double* eext;  // [32] elite extinction by column
     double* f0s;   // [32] best_curr fitness per problem
@@ -52,22 +57,29 @@ struct WarpSmem {
     int* ctl;      // [4]
 };
 
-__host__ __device__ inline size_t warp_smem_bytes(int n, int P) {
-    size_t d = (size_t)5 * n * kS + (size_t)2 * n * 16 + (size_t)P + 32 * 7 + 3 * 32;
+// fit aliases the sc rows (dead once the elite searches are done) when the population fits there
+__host__ __device__ inline bool fit_in_sc(int n, int P) { return P <= 2 * n * kS; }
+
+__host__ __device__ inline size_t warp_smem_bytes(int n, int P, int PW) {
+    size_t d = (size_t)5 * n * kS + (fit_in_sc(n, P) ? 0 : (size_t)P) + (size_t)PW * 7 + 3 * 32;
     size_t i = 32 + 33 + 32 + 32 + 4;
     return ((d * 8 + i * 4) + 15) & ~size_t(15);
 }
 
-__device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P) {
+__device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P, int PW) {
     WarpSmem W;
     double* d = reinterpret_cast<double*>(base);
     W.q = d; d += (size_t)n * kS;
     W.g = d; d += (size_t)n * kS;
     W.best = d; d += (size_t)n * kS;
     W.sc = d; d += (size_t)2 * n * kS;
-    W.cs = d; d += (size_t)2 * n * 16;
-    W.fit = d; d += P;
-    W.goal = d; d += 32 * 7;
+    W.cs = W.sc + 16;
+    if (fit_in_sc(n, P)) {
+        W.fit = W.sc;
+    } else {
+        W.fit = d; d += P;
+    }
+    W.goal = d; d += PW * 7;
     W.efit = d; d += 32;
     W.eext = d; d += 32;
     W.f0s = d; d += 32;
@@ -259,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n, P = c_pr.P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P), n, P);
+    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, PW), n, P, PW);
     const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * PW;
     if (base >= sb.B) return;
     bool keep = false;
@@ -346,14 +358,14 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
             if (act && k < 2 * n) {
                 const int i = k >> 1;
                 const double qi = q[i * kS];
-                W.cs[k * 16 + c] = eval_chain(q, nullptr, kViewFd, i, (k & 1) ? qi + h : qi - h, sc, nullptr, g7, sd, nullptr);
+                W.cs[k * kS + c] = eval_chain(q, nullptr, kViewFd, i, (k & 1) ? qi + h : qi - h, sc, nullptr, g7, sd, nullptr);
             }
         }
         __syncwarp();
         if (act && leader) {
             double sum = h;
             for (int i = 0; i < n; ++i) {
-                const double gi = W.cs[(2 * i + 1) * 16 + c] - W.cs[(2 * i) * 16 + c];
+                const double gi = W.cs[(2 * i + 1) * kS + c] - W.cs[(2 * i) * kS + c];
                 g[i * kS] = gi;
                 sum = sum + fabs(gi);
             }
@@ -361,10 +373,10 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
         }
         __syncwarp();
         if (act && gl < 2 && gl < L)
-            W.cs[gl * 16 + c] = eval_chain(q, g, gl == 0 ? kViewMinus : kViewPlus, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
+            W.cs[gl * kS + c] = eval_chain(q, g, gl == 0 ? kViewMinus : kViewPlus, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
         __syncwarp();
         if (act && leader) {
-            accept_step(q, g, W.cs[c], W.cs[16 + c]);
+            accept_step(q, g, W.cs[c], W.cs[kS + c]);
             local_cost = eval_chain(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
             if (local_cost < best_cost) {
                 for (int j = 0; j < n; ++j) best[j * kS] = q[j * kS];
@@ -388,7 +400,7 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
 // -----------------------------------------------------------------------------------------------
 // One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for PW problems per warp.
 // -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
+__global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
                                                                       int list_in, int L, int PW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
@@ -396,7 +408,7 @@ __global__ void __launch_bounds__(kThreads) memetic_generation_kernel(const __gr
     const int n_active = sb.counters[list_in];
     const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * PW;
     if (base >= n_active) return;
-    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P), n, P);
+    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, PW), n, P, PW);
     const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;
     int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
 
@@ -769,7 +781,7 @@ MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
     if (L > memetic_max_lanes_per_elite(E)) L = memetic_max_lanes_per_elite(E);
     s.lanes_per_elite = L;
     s.problems_per_warp = 32 / (E * L);
-    s.smem = kWarpsPerBlock * warp_smem_bytes(n, P);
+    s.smem = kWarpsPerBlock * warp_smem_bytes(n, P, s.problems_per_warp);
     return s;
 }
 
