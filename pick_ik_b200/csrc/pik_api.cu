@@ -32,6 +32,7 @@ struct DeviceArray {
 struct pik_solver {
     pik_robot robot;
     int device = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -83,13 +84,25 @@ bool finite_ge(double v, double lo) { return v == v && v >= lo; }
 // launch kernels are serialised per process.
 std::mutex g_launch_mutex;
 
-// Active-problem count at or below which a generation runs in latency mode (several lanes per elite).
-int64_t wide_threshold() {
-    static const int64_t v = [] {
-        const char* e = std::getenv("PIK_WIDE_THRESHOLD");
-        return e ? std::atoll(e) : (int64_t)6144;
-    }();
+bool trace_enabled() {
+    static const bool v = std::getenv("PIK_TRACE") != nullptr;
     return v;
+}
+
+// Lanes per elite for a generation over n_active problems: the largest power of two (up to the warp's
+// capacity) that still lets every problem's warps be resident at once -- below that point the batch is
+// latency-bound and spreading one GD step over more lanes is free; above it lanes are better spent on
+// whole GD instances (throughput mode, 1 lane per elite).
+int lanes_for(int64_t n_active, int E, int sm_count) {
+    static const int64_t warps_per_sm = [] {
+        const char* e = std::getenv("PIK_WIDE_WARPS_PER_SM");
+        return e ? std::atoll(e) : (int64_t)12;
+    }();
+    const int64_t capacity_lanes = (int64_t)sm_count * warps_per_sm * 32;
+    const int lmax = memetic_max_lanes_per_elite(E);
+    int L = 1;
+    while (L * 2 <= lmax && n_active * E * (L * 2) <= capacity_lanes) L *= 2;
+    return L;
 }
 
 }  // namespace
@@ -256,6 +269,7 @@ int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_counters), 2 * sizeof(int32_t), cudaHostAllocDefault);
     if (e == cudaSuccess)
         e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_stats), 4 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = configure_kernels();
     if (e != cudaSuccess) {
         std::fprintf(stderr, "pik_solver_create: %s\n", cudaGetErrorString(e));
@@ -369,7 +383,7 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
         for (int gen = 0; gen < pr.max_generations && n_active > 0; ++gen) {
             PIK_CUDA(s, cudaMemsetAsync(sb.counters + (list ^ 1), 0, sizeof(int32_t), st));
             PIK_CUDA(s, cudaEventRecord(s->ev2, st));
-            const int lanes = n_active <= wide_threshold() ? memetic_max_lanes_per_elite(pr.E) : 1;
+            const int lanes = lanes_for(n_active, pr.E, s->sm_count);
             PIK_CUDA(s, launch_memetic_generation(st, n, P, pr.E, sb, list, n_active, lanes));
             PIK_CUDA(s, cudaEventRecord(s->ev3, st));
             s->stats.kernel_launches += 1;
@@ -380,6 +394,8 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
             float gms = 0.f;
             PIK_CUDA(s, cudaEventElapsedTime(&gms, s->ev2, s->ev3));
             s->stats.generation_ms += gms;
+            if (trace_enabled())
+                std::fprintf(stderr, "pik gen %3d active %8lld lanes %2d  %8.3f ms\n", gen, (long long)n_active, lanes, gms);
             n_active = s->h_counters[list ^ 1];
             list ^= 1;
         }

@@ -30,7 +30,7 @@ namespace pik {
 namespace {
 
 #ifndef PIK_GEN_MIN_BLOCKS
-#define PIK_GEN_MIN_BLOCKS 4
+#define PIK_GEN_MIN_BLOCKS 3
 #endif
 
 constexpr int kWarpsPerBlock = 4;
@@ -132,7 +132,11 @@ __global__ void __launch_bounds__(kThreads) eval_cost_kernel(int64_t B, const do
     Frame F;
     frame_load_origin(F, 0);
 #pragma unroll 1
-    for (int j = 0; j < n; ++j) walk_joint(F, j, j > 0, cv.at(j), true, nullptr, nullptr);
+    for (int j = 0; j < n; ++j) {
+        double sj, cj;
+        joint_sincos(j, cv.at(j), sj, cj);
+        walk_joint(F, j, j > 0, cv.at(j), sj, cj);
+    }
     if (c_rb.has_tip) frame_mul_const(F, c_rb.tip_R, c_rb.tip_t);
     double aux[5];
     const double c = total_cost(g7, F, cv, sd, aux);
