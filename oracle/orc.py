@@ -14,13 +14,26 @@ LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
 MAX_VARS = 16
 
 
+def _source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in ("pik_oracle.c", "pik_oracle.h", "Makefile"):
+        with open(os.path.join(HERE, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False) -> str:
-    src = [os.path.join(HERE, f) for f in ("pik_oracle.c", "pik_oracle.h")]
-    if not force and os.path.exists(LIB_PATH) and all(
-        os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src
-    ):
-        return LIB_PATH
+    """Compiles the oracle when its sources changed (content hash: mtimes do not survive a copy)."""
+    stamp = LIB_PATH + ".hash"
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
+        with open(stamp) as fh:
+            if fh.read().strip() == _source_hash():
+                return LIB_PATH
     subprocess.check_call(["make", "-C", HERE, "-B", "_build/liboracle.so"], stdout=subprocess.DEVNULL)
+    with open(stamp, "w") as fh:
+        fh.write(_source_hash())
     return LIB_PATH
 
 

@@ -1,0 +1,172 @@
+// pick_ik_plugin.hpp -- host-side mirror of the reference's plugin surface over the C-ABI (include/pik.h).
+//
+// The reference's drop-in entry is pick_ik::PickIKPlugin : kinematics::KinematicsBase
+// (include/pick_ik/pick_ik_plugin.hpp:10-102, src/pick_ik_plugin.cpp:22-401).  MoveIt, rclcpp and the ROS
+// message packages are not available in this environment, so the MoveIt types the interface names are
+// declared here as minimal stand-ins with the same member names (namespace pick_ik_b200::compat); a MoveIt
+// build replaces this header's `compat` types by the real ones.  Method names, argument
+// order and meaning, return values and error codes follow the reference; every method cites what it mirrors.
+//
+// What is behind it differs: the solve runs on the GPU through pik_solve_batch, and the class also
+// offers the batched entry point the reference does not have (searchPositionIKBatch).
+#pragma once
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pik.h"
+
+namespace pick_ik_b200 {
+
+namespace compat {
+
+// geometry_msgs::msg::Pose
+struct Point {
+    double x = 0.0, y = 0.0, z = 0.0;
+};
+struct Quaternion {
+    double x = 0.0, y = 0.0, z = 0.0, w = 1.0;
+};
+struct Pose {
+    Point position;
+    Quaternion orientation;
+};
+
+// moveit_msgs::msg::MoveItErrorCodes (the two values the plugin writes, src/pick_ik_plugin.cpp:212,215)
+struct MoveItErrorCodes {
+    static constexpr int SUCCESS = 1;
+    static constexpr int NO_IK_SOLUTION = -31;
+    int val = 0;
+};
+
+// kinematics::KinematicsQueryOptions (only return_approximate_solution is read, src/pick_ik_plugin.cpp:187,199,222)
+struct KinematicsQueryOptions {
+    bool lock_redundant_joints = false;
+    bool return_approximate_solution = false;
+};
+
+// kinematics::KinematicsBase::IKCallbackFn
+using IKCallbackFn = std::function<void(Pose const&, std::vector<double> const&, MoveItErrorCodes&)>;
+
+// What the plugin reads from moveit::core::RobotModel + JointModelGroup (src/pick_ik_plugin.cpp:42-68,
+// src/robot.cpp:44-85,107-160): the serial chain of the group from the model root to its tip link.
+struct ChainModel {
+    std::string group_name;
+    std::string model_frame;               // RobotModel::getModelFrame()
+    std::vector<pik_joint_desc> joints;    // chain order, fixed joints included
+    std::vector<std::string> joint_names;  // one per entry of `joints`
+    std::vector<std::string> link_names;   // child link of each joint; the last one is the tip link
+};
+
+}  // namespace compat
+
+// pick_ik::Params (generated from src/pick_ik_parameters.yaml by generate_parameter_library): same member
+// names, same defaults.  The reference re-reads them on every solve (src/pick_ik_plugin.cpp:86); here the
+// caller sets them on the plugin (setParams / loadParams) and they are read on every solve.
+struct Params {
+    std::string mode = "global";
+    double gd_step_size = 0.0001;
+    int gd_max_iters = 100;
+    double gd_min_cost_delta = 1.0e-12;
+    double position_threshold = 0.001;
+    double orientation_threshold = 0.001;
+    double approximate_solution_position_threshold = 0.05;
+    double approximate_solution_orientation_threshold = 0.05;
+    double approximate_solution_joint_threshold = 0.0;
+    double approximate_solution_cost_threshold = 0.0;
+    double cost_threshold = 0.001;
+    double position_scale = 1.0;
+    double rotation_scale = 0.5;
+    double center_joints_weight = 0.0;
+    double avoid_joint_limits_weight = 0.0;
+    double minimal_displacement_weight = 0.0;
+    bool stop_optimization_on_valid_solution = true;
+    int memetic_num_threads = 1;
+    bool memetic_stop_on_first_solution = true;
+    int memetic_population_size = 16;
+    int memetic_elite_size = 4;
+    double memetic_wipeout_fitness_tol = 0.00001;
+    int memetic_max_generations = 100;
+    int memetic_gd_max_iters = 25;
+    double memetic_gd_max_time = 0.005;
+    unsigned long long rng_seed = 0x5EED;  // not a reference parameter: the reference's RNG is unseeded
+};
+
+// Sets one parameter by its YAML name from text ("true"/"false" for bools).  Returns false for an unknown
+// name or an unparsable value.
+bool set_param(Params& p, std::string const& name, std::string const& value);
+// Reads "name: value" lines (a flat override file, or the `default_value` entries of
+// pick_ik_parameters.yaml).  Returns the number of parameters set, or -1 on a malformed line.
+int load_params(Params& p, std::string const& text);
+// The YAML -> C-ABI mapping (mode string -> enum etc.).  Returns false when `mode` is invalid.
+bool to_pik_params(Params const& p, bool return_approximate_solution, pik_params& out);
+
+class PickIKPlugin {
+   public:
+    PickIKPlugin();
+    ~PickIKPlugin();
+    PickIKPlugin(PickIKPlugin const&) = delete;
+    PickIKPlugin& operator=(PickIKPlugin const&) = delete;
+
+    // kinematics::KinematicsBase::initialize (include/pick_ik/pick_ik_plugin.hpp:24-29,
+    // src/pick_ik_plugin.cpp:22-71).  Throws std::invalid_argument when a tip frame is not a link of the
+    // chain (src/pick_ik_plugin.cpp:65-67).  `device` selects the GPU (no reference counterpart).
+    bool initialize(compat::ChainModel const& robot_model, std::string const& group_name,
+                    std::string const& base_frame, std::vector<std::string> const& tip_frames,
+                    double search_discretization, int device = 0);
+
+    // The main overload (include/pick_ik/pick_ik_plugin.hpp:31-41, src/pick_ik_plugin.cpp:73-294).  The
+    // custom IKCostFn of the reference is a host callback over a RobotState and cannot run on the device: not
+    // offered.  consistency_limits and context_state are ignored, as in the reference.
+    bool searchPositionIK(std::vector<compat::Pose> const& ik_poses, std::vector<double> const& ik_seed_state,
+                          double timeout, std::vector<double> const& consistency_limits,
+                          std::vector<double>& solution, compat::IKCallbackFn const& solution_callback,
+                          compat::MoveItErrorCodes& error_code,
+                          compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
+
+    // Forwarding overloads (include/pick_ik/pick_ik_plugin.hpp:57-102, src/pick_ik_plugin.cpp:314-401)
+    bool searchPositionIK(compat::Pose const& ik_pose, std::vector<double> const& ik_seed_state, double timeout,
+                          std::vector<double>& solution, compat::MoveItErrorCodes& error_code,
+                          compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
+    bool searchPositionIK(compat::Pose const& ik_pose, std::vector<double> const& ik_seed_state, double timeout,
+                          std::vector<double> const& consistency_limits, std::vector<double>& solution,
+                          compat::MoveItErrorCodes& error_code,
+                          compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
+    bool searchPositionIK(compat::Pose const& ik_pose, std::vector<double> const& ik_seed_state, double timeout,
+                          std::vector<double>& solution, compat::IKCallbackFn const& solution_callback,
+                          compat::MoveItErrorCodes& error_code,
+                          compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
+    bool searchPositionIK(compat::Pose const& ik_pose, std::vector<double> const& ik_seed_state, double timeout,
+                          std::vector<double> const& consistency_limits, std::vector<double>& solution,
+                          compat::IKCallbackFn const& solution_callback, compat::MoveItErrorCodes& error_code,
+                          compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
+
+    // Batched form of the main overload (new): B independent problems, one pose and one seed each, solved in
+    // one pik_solve_batch call.  solutions [B][n]; error_codes [B].  Returns the number of problems solved, or
+    // -1 on an invalid mode / engine error.  Applies the same approximate-solution gating per problem.
+    long searchPositionIKBatch(std::vector<compat::Pose> const& ik_poses,
+                               std::vector<std::vector<double>> const& ik_seed_states,
+                               std::vector<std::vector<double>>& solutions,
+                               std::vector<compat::MoveItErrorCodes>& error_codes,
+                               compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
+
+    std::vector<std::string> const& getJointNames() const;  // src/pick_ik_plugin.cpp:296
+    std::vector<std::string> const& getLinkNames() const;   // src/pick_ik_plugin.cpp:298
+    // src/pick_ik_plugin.cpp:300-312: not implemented by the reference either
+    bool getPositionFK(std::vector<std::string> const&, std::vector<double> const&, std::vector<compat::Pose>&) const;
+    bool getPositionIK(compat::Pose const&, std::vector<double> const&, std::vector<double>&,
+                       compat::MoveItErrorCodes&, compat::KinematicsQueryOptions const&) const;
+
+    void setParams(Params const& p);
+    Params const& getParams() const;
+    std::string const& lastError() const;
+
+   private:
+    struct Impl;
+    std::unique_ptr<Impl> impl_;
+};
+
+}  // namespace pick_ik_b200

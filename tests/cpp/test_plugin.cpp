@@ -1,0 +1,272 @@
+// test_plugin.cpp -- the host-side PickIKPlugin mirror, exercised the way the reference exercises its
+// solvers (tests/ik_tests.cpp:137-293, tests/ik_memetic_tests.cpp:110-206) but through the plugin surface
+// (which the reference itself does not test).  `--cpu-only` runs the sections that need no GPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../pick_ik_b200/host/pick_ik_plugin.hpp"
+
+using namespace pick_ik_b200;
+using compat::ChainModel;
+using compat::KinematicsQueryOptions;
+using compat::MoveItErrorCodes;
+using compat::Pose;
+
+static int g_failures = 0, g_checks = 0;
+#define CHECK(cond)                                                                 \
+    do {                                                                            \
+        ++g_checks;                                                                 \
+        if (!(cond)) {                                                              \
+            ++g_failures;                                                           \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);           \
+        }                                                                           \
+    } while (0)
+static bool approx(double a, double b, double margin) { return std::fabs(a - b) <= margin; }
+
+// urdfdom setFromRPY -> quaternion -> rotation matrix
+static void rpy_to_matrix(double r, double p, double y, double* R) {
+    double const phi = r / 2, the = p / 2, psi = y / 2;
+    double qx = std::sin(phi) * std::cos(the) * std::cos(psi) - std::cos(phi) * std::sin(the) * std::sin(psi);
+    double qy = std::cos(phi) * std::sin(the) * std::cos(psi) + std::sin(phi) * std::cos(the) * std::sin(psi);
+    double qz = std::cos(phi) * std::cos(the) * std::sin(psi) - std::sin(phi) * std::sin(the) * std::cos(psi);
+    double qw = std::cos(phi) * std::cos(the) * std::cos(psi) + std::sin(phi) * std::sin(the) * std::sin(psi);
+    double const nrm = std::sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+    qx /= nrm; qy /= nrm; qz /= nrm; qw /= nrm;
+    double const tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    double const txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+
+static void add_joint(ChainModel& m, char const* joint, char const* link, int type, double x, double y, double z,
+                      double rr, double rp, double ry, double lower, double upper, double vel) {
+    pik_joint_desc jd;
+    std::memset(&jd, 0, sizeof(jd));
+    jd.type = type;
+    jd.bounded = type != PIK_JOINT_FIXED;
+    rpy_to_matrix(rr, rp, ry, jd.origin_R);
+    jd.origin_t[0] = x; jd.origin_t[1] = y; jd.origin_t[2] = z;
+    jd.axis[2] = 1.0;
+    jd.min_position = lower; jd.max_position = upper; jd.max_velocity = vel;
+    m.joints.push_back(jd);
+    m.joint_names.push_back(joint);
+    m.link_names.push_back(link);
+}
+
+// tests/ik_tests.cpp:15-48: base -> a (revolute z), a -> b (revolute z, x = 2), b -> ee (fixed, x = 1)
+static ChainModel make_rr_model_for_ik() {
+    ChainModel m;
+    m.group_name = "group";
+    m.model_frame = "base";
+    add_joint(m, "base-a-joint", "a", PIK_JOINT_REVOLUTE, 0, 0, 0, 0, 0, 0, -M_PI, M_PI, 0);
+    add_joint(m, "a-b-joint", "b", PIK_JOINT_REVOLUTE, 2, 0, 0, 0, 0, 0, -M_PI, M_PI, 0);
+    add_joint(m, "b-ee-joint", "ee", PIK_JOINT_FIXED, 1, 0, 0, 0, 0, 0, 0, 0, 0);
+    return m;
+}
+
+// moveit_resources panda, group panda_arm + panda_hand
+static ChainModel make_panda_model() {
+    double const H = 1.57079632679;
+    ChainModel m;
+    m.group_name = "panda_arm";
+    m.model_frame = "panda_link0";
+    add_joint(m, "panda_joint1", "panda_link1", PIK_JOINT_REVOLUTE, 0, 0, 0.333, 0, 0, 0, -2.8973, 2.8973, 2.1750);
+    add_joint(m, "panda_joint2", "panda_link2", PIK_JOINT_REVOLUTE, 0, 0, 0, -H, 0, 0, -1.7628, 1.7628, 2.1750);
+    add_joint(m, "panda_joint3", "panda_link3", PIK_JOINT_REVOLUTE, 0, -0.316, 0, H, 0, 0, -2.8973, 2.8973, 2.1750);
+    add_joint(m, "panda_joint4", "panda_link4", PIK_JOINT_REVOLUTE, 0.0825, 0, 0, H, 0, 0, -3.0718, -0.0698, 2.1750);
+    add_joint(m, "panda_joint5", "panda_link5", PIK_JOINT_REVOLUTE, -0.0825, 0.384, 0, -H, 0, 0, -2.8973, 2.8973, 2.6100);
+    add_joint(m, "panda_joint6", "panda_link6", PIK_JOINT_REVOLUTE, 0, 0, 0, H, 0, 0, -0.0175, 3.7525, 2.6100);
+    add_joint(m, "panda_joint7", "panda_link7", PIK_JOINT_REVOLUTE, 0.088, 0, 0, H, 0, 0, -2.8973, 2.8973, 2.6100);
+    add_joint(m, "panda_joint8", "panda_link8", PIK_JOINT_FIXED, 0, 0, 0.107, 0, 0, 0, 0, 0, 0);
+    add_joint(m, "panda_hand_joint", "panda_hand", PIK_JOINT_FIXED, 0, 0, 0, 0, 0, -0.785398163397, 0, 0, 0);
+    return m;
+}
+
+static Pose make_pose(double x, double y, double z, double qw, double qx, double qy, double qz) {
+    Pose p;
+    p.position.x = x; p.position.y = y; p.position.z = z;
+    p.orientation.w = qw; p.orientation.x = qx; p.orientation.y = qy; p.orientation.z = qz;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+static void test_params(std::string const& yaml_path) {
+    Params p;
+    CHECK(set_param(p, "mode", "local") && p.mode == "local");
+    CHECK(set_param(p, "memetic_population_size", "128") && p.memetic_population_size == 128);
+    CHECK(set_param(p, "stop_optimization_on_valid_solution", "false") && !p.stop_optimization_on_valid_solution);
+    CHECK(!set_param(p, "no_such_parameter", "1"));
+    CHECK(!set_param(p, "gd_max_iters", "many"));
+    Params q;
+    CHECK(load_params(q, "mode: local\n# comment\nrotation_scale: 0.25\n") == 2);
+    CHECK(q.mode == "local" && q.rotation_scale == 0.25);
+    CHECK(load_params(q, "this is not yaml") == -1);
+    // the parameter contract file parses back to the built-in defaults
+    std::ifstream in(yaml_path);
+    CHECK(in.good());
+    std::stringstream ss;
+    ss << in.rdbuf();
+    Params y;
+    y.mode = "";
+    y.memetic_gd_max_iters = -1;
+    CHECK(load_params(y, ss.str()) == 25);
+    Params def;
+    CHECK(y.mode == def.mode && y.memetic_gd_max_iters == def.memetic_gd_max_iters && y.rotation_scale == def.rotation_scale &&
+          y.memetic_population_size == def.memetic_population_size && y.gd_min_cost_delta == def.gd_min_cost_delta);
+    pik_params pp;
+    CHECK(to_pik_params(def, false, pp) && pp.mode == PIK_MODE_GLOBAL && pik_params_validate(&pp) == PIK_OK);
+    def.mode = "sideways";
+    CHECK(!to_pik_params(def, false, pp));
+}
+
+static void test_initialize_errors(bool have_gpu) {
+    PickIKPlugin plugin;
+    auto const model = make_rr_model_for_ik();
+    bool threw = false;
+    try {
+        plugin.initialize(model, "group", "base", {"no_such_link"}, 0.0);
+    } catch (std::invalid_argument const&) {
+        threw = true;  // src/pick_ik_plugin.cpp:65-67
+    }
+    CHECK(threw);
+    CHECK(!plugin.initialize(model, "other_group", "base", {"ee"}, 0.0));
+    if (!have_gpu) CHECK(!plugin.initialize(model, "group", "base", {"ee"}, 0.0));  // no device: fails, no CPU fallback
+    std::vector<Pose> out;
+    CHECK(!plugin.getPositionFK({}, {}, out));  // src/pick_ik_plugin.cpp:300-305
+}
+
+// tests/ik_tests.cpp:137-238 through the plugin, local mode, IkTestParams (:78-86)
+static void test_rr_ik() {
+    PickIKPlugin plugin;
+    CHECK(plugin.initialize(make_rr_model_for_ik(), "group", "base", {"ee"}, 0.0));
+    CHECK(plugin.getJointNames().size() == 2 && plugin.getLinkNames().size() == 1 && plugin.getLinkNames()[0] == "ee");
+    Params p;
+    p.mode = "local";
+    p.position_threshold = 0.0001;
+    p.orientation_threshold = 0.001;
+    p.cost_threshold = 0.0001;
+    p.rotation_scale = 1.0;
+    plugin.setParams(p);
+    double const s45 = std::sin(M_PI_4);
+    struct Case { Pose goal; double e0, e1, g0, g1; bool solvable; };
+    Pose const goal_a = make_pose(3, 0, 0, 1, 0, 0, 0);
+    Pose const goal_b = make_pose(s45, 3 * s45, 0, std::cos(0.375 * M_PI), 0, 0, std::sin(0.375 * M_PI));
+    std::vector<Case> cases = {
+        {goal_a, 0, 0, 0.1, -0.1, true},                      // :140-151
+        {goal_a, 0, 0, M_PI_2, -M_PI_2, true},                // :153-164
+        {goal_b, M_PI_4, M_PI_2, M_PI_4 + 0.1, M_PI_2 - 0.1, true},  // :166-178
+        {goal_b, M_PI_4, M_PI_2, 0, 0, true},                 // :180-192
+        {make_pose(0, 0, 0, 1, 0, 0, 0), 0, 0, 0, 0, false},  // :194-203 unreachable
+        {make_pose(s45, 3 * s45, 0, 1, 0, 0, 0), 0, 0, 0, 0, false},  // :205-216 position yes, orientation no
+    };
+    for (auto const& c : cases) {
+        std::vector<double> sol;
+        MoveItErrorCodes ec;
+        bool const ok = plugin.searchPositionIK(c.goal, {c.g0, c.g1}, 0.05, sol, ec);
+        CHECK(ok == c.solvable);
+        CHECK(ec.val == (c.solvable ? MoveItErrorCodes::SUCCESS : MoveItErrorCodes::NO_IK_SOLUTION));
+        if (c.solvable) {
+            CHECK(approx(sol[0], c.e0, 0.01) && approx(sol[1], c.e1, 0.01));
+        } else {
+            CHECK(sol.size() == 2 && sol[0] == c.g0 && sol[1] == c.g1);  // solution = seed on failure, :216
+        }
+    }
+    // :218-233 zero rotation scale makes the last goal solvable
+    p.rotation_scale = 0.0;
+    plugin.setParams(p);
+    std::vector<double> sol;
+    MoveItErrorCodes ec;
+    CHECK(plugin.searchPositionIK(make_pose(s45, 3 * s45, 0, 1, 0, 0, 0), {M_PI_4 + 0.1, M_PI_2 - 0.1}, 0.05, sol, ec));
+    CHECK(approx(sol[0], M_PI_4, 0.01) && approx(sol[1], M_PI_2, 0.01));
+    // invalid mode: error + false (src/pick_ik_plugin.cpp:204-207)
+    p.mode = "sideways";
+    plugin.setParams(p);
+    CHECK(!plugin.searchPositionIK(goal_a, {0.1, -0.1}, 0.05, sol, ec));
+}
+
+// tests/ik_memetic_tests.cpp:110-206 through the plugin (global mode), plus callback veto and the batch entry
+static void test_panda_memetic() {
+    PickIKPlugin plugin;
+    CHECK(plugin.initialize(make_panda_model(), "panda_arm", "panda_link0", {"panda_hand"}, 0.0));
+    CHECK(plugin.getJointNames().size() == 7);
+    std::vector<double> const home = {0.0, -M_PI_4, 0.0, -3.0 * M_PI_4, 0.0, M_PI_2, M_PI_4};
+    // FK(home) of panda_hand: t = (0.306891, 0, 0.590282), R = Rx(pi) . Rz(...) -> q(w,x,y,z) = (0, 1, 0, 0)
+    // (SURVEY.md App. C sanity values)
+    Pose const goal = make_pose(0.30689059, 0.0, 0.59028174, 0.0, 1.0, 0.0, 0.0);
+    Params p;  // yaml defaults: global, P = 16, E = 4
+    p.position_threshold = 0.001;
+    plugin.setParams(p);
+    std::vector<std::vector<double>> guesses = {home, {0.1, -M_PI_4 - 0.1, 0.0, -3.0 * M_PI_4 + 0.1, -0.1, M_PI_2, M_PI_4 + 0.1},
+                                                {0, 0, 0, 0, 0, 0, 0}};
+    for (auto const& g : guesses) {
+        std::vector<double> sol;
+        MoveItErrorCodes ec;
+        CHECK(plugin.searchPositionIK(goal, g, 1.0, sol, ec));
+        CHECK(ec.val == MoveItErrorCodes::SUCCESS && sol.size() == 7);
+    }
+    // four species (":174-190 multithreaded"), and with the joint-centering / limit-avoiding goals (:192-213)
+    p.memetic_num_threads = 4;
+    plugin.setParams(p);
+    std::vector<double> sol;
+    MoveItErrorCodes ec;
+    CHECK(plugin.searchPositionIK(goal, {0, 0, 0, 0, 0, 0, 0}, 1.0, sol, ec));
+    p.memetic_num_threads = 1;
+    p.center_joints_weight = 0.01;
+    p.avoid_joint_limits_weight = 0.01;
+    p.cost_threshold = 0.01;
+    p.position_threshold = 0.01;
+    plugin.setParams(p);
+    CHECK(plugin.searchPositionIK(goal, {0, 0, 0, 0, 0, 0, 0}, 1.0, sol, ec));
+    // the callback runs only on success and may veto (src/pick_ik_plugin.cpp:270-274)
+    int calls = 0;
+    auto veto = [&](Pose const&, std::vector<double> const&, MoveItErrorCodes& e) {
+        ++calls;
+        e.val = MoveItErrorCodes::NO_IK_SOLUTION;
+    };
+    CHECK(!plugin.searchPositionIK(goal, home, 0.0, sol, veto, ec));
+    CHECK(calls == 1 && ec.val == MoveItErrorCodes::NO_IK_SOLUTION);
+    // batch entry: 64 copies of the problem from different seeds
+    std::vector<Pose> poses(64, goal);
+    std::vector<std::vector<double>> seeds(64, home), sols;
+    for (int b = 0; b < 64; ++b) seeds[b][0] += 0.01 * b;
+    std::vector<MoveItErrorCodes> codes;
+    long const solved = plugin.searchPositionIKBatch(poses, seeds, sols, codes);
+    CHECK(solved >= 60 && sols.size() == 64 && codes.size() == 64);
+    // approximate-solution gating: an unreachable pose fails the (strict) frame tests, seed comes back
+    KinematicsQueryOptions opt;
+    opt.return_approximate_solution = true;
+    p = Params();
+    p.memetic_max_generations = 3;
+    plugin.setParams(p);
+    CHECK(!plugin.searchPositionIK({make_pose(5, 5, 5, 1, 0, 0, 0)}, home, 0.0, {}, sol, compat::IKCallbackFn(), ec, opt));
+    CHECK(ec.val == MoveItErrorCodes::NO_IK_SOLUTION && sol == home);
+}
+
+int main(int argc, char** argv) {
+    bool cpu_only = false;
+    std::string yaml = "pick_ik_b200/host/pick_ik_parameters.yaml";
+    for (int i = 1; i < argc; ++i) {
+        if (std::string(argv[i]) == "--cpu-only") cpu_only = true;
+        else yaml = argv[i];
+    }
+    bool const have_gpu = pik_device_count() > 0;
+    test_params(yaml);
+    test_initialize_errors(have_gpu);
+    if (!cpu_only) {
+        if (!have_gpu) {
+            std::printf("no CUDA device: the solve sections need one\n");
+            return 2;
+        }
+        test_rr_ik();
+        test_panda_memetic();
+    }
+    std::printf("%d checks, %d failures\n", g_checks, g_failures);
+    return g_failures == 0 ? 0 : 1;
+}
