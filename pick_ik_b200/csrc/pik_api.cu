@@ -33,6 +33,7 @@ struct pik_solver {
     pik_robot robot;
     int device = 0;
     int sm_count = 148;
+    int spec = 0;  // compiled chain signature matching the robot (select_spec)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -253,6 +254,7 @@ int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_
     if (!s) return PIK_E_OUT_OF_MEMORY;
     s->robot = *robot;
     s->device = device;
+    s->spec = select_spec(robot->dev);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) {
         if (stream) {
@@ -370,11 +372,11 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
     }
     PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 4 * sizeof(unsigned long long), st));
     if (!global) {
-        PIK_CUDA(s, launch_gd_local(st, n, sb));
+        PIK_CUDA(s, launch_gd_local(st, s->spec, n, sb));
         s->stats.kernel_launches += 1;
     } else {
         PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, 2 * sizeof(int32_t), st));
-        PIK_CUDA(s, launch_memetic_init(st, n, P, pr.E, sb));
+        PIK_CUDA(s, launch_memetic_init(st, s->spec, n, P, pr.E, sb));
         s->stats.kernel_launches += 1;
         PIK_CUDA(s, cudaMemcpyAsync(s->h_counters, sb.counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         PIK_CUDA(s, cudaStreamSynchronize(st));
@@ -384,7 +386,7 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
             PIK_CUDA(s, cudaMemsetAsync(sb.counters + (list ^ 1), 0, sizeof(int32_t), st));
             PIK_CUDA(s, cudaEventRecord(s->ev2, st));
             const int lanes = lanes_for(n_active, pr.E, s->sm_count);
-            PIK_CUDA(s, launch_memetic_generation(st, n, P, pr.E, sb, list, n_active, lanes));
+            PIK_CUDA(s, launch_memetic_generation(st, s->spec, n, P, pr.E, sb, list, n_active, lanes));
             PIK_CUDA(s, cudaEventRecord(s->ev3, st));
             s->stats.kernel_launches += 1;
             s->stats.generation_launches += 1;

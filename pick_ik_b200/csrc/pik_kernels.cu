@@ -22,6 +22,8 @@
 #include "pik_kernels.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
+#include <cstdlib>
 
 #include "pik_device.cuh"
 
@@ -134,8 +136,8 @@ __global__ void __launch_bounds__(kThreads) eval_cost_kernel(int64_t B, const do
 #pragma unroll 1
     for (int j = 0; j < n; ++j) {
         double sj, cj;
-        joint_sincos(j, cv.at(j), sj, cj);
-        walk_joint(F, j, j > 0, cv.at(j), sj, cj);
+        joint_sincos<GenericSpec>(j, cv.at(j), sj, cj);
+        walk_joint<GenericSpec>(F, j, j > 0, cv.at(j), sj, cj);
     }
     if (c_rb.has_tip) frame_mul_const(F, c_rb.tip_R, c_rb.tip_t);
     double aux[5];
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(kThreads) eval_cost_kernel(int64_t B, const do
 // -----------------------------------------------------------------------------------------------
 // ik_gradient (src/ik_gradient.cpp:96-139), one problem per lane, whole loop on chip
 // -----------------------------------------------------------------------------------------------
+template <class S>
 __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constant__ SolveBuffers sb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
     }
     goal_from_pose(sb.goal_pose + 7 * b, g7);
     double aux[5];
-    const double c0 = eval_chain(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, aux);
+    const double c0 = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, aux);
     bool found = false;
     int iters = 0;
     unsigned long long steps = 0;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
         st.local_cost = st.best_cost = c0;  // GradientIk::from
         double previous_cost = 0.0;
         while (iters < c_pr.gd_max_iters) {
-            const bool improved = gd_step(st, g7, sd, aux);
+            const bool improved = gd_step<S>(st, g7, sd, aux);
             ++steps;
             // best == local when improved, so aux describes best (ik_gradient.cpp:117-121)
             if (improved && c_pr.stop_on_valid && solution_from_aux(aux)) {
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
             ++iters;
         }
         if (!found && !c_pr.stop_on_valid) {  // ik_gradient.cpp:130-132
-            eval_chain(st.best, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
+            eval_chain<S>(st.best, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
             found = solution_from_aux(aux);
         }
         if (!found && c_pr.approx) found = true;  // ik_gradient.cpp:134-136
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
 // are new.  Extinctions are computed on this unsorted population as the reference does.  Called by all
 // lanes of the warp.
 // -----------------------------------------------------------------------------------------------
+template <class S>
 __device__ __forceinline__ void init_population_warp(const SolveBuffers& sb, const WarpSmem& W, int PW, int lane) {
     const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
     const int k_e = lane / E, e = lane % E;
@@ -234,7 +238,7 @@ __device__ __forceinline__ void init_population_warp(const SolveBuffers& sb, con
             const Stream st = make_stream((uint32_t)(sb.first_problem_index + b), kStreamInit, (uint32_t)m.init_epoch,
                                           (uint32_t)e);
             random_valid_configuration(st, col);
-            f = eval_chain(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k_e,
+            f = eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k_e,
                            sb.seed + b * sb.seed_stride, nullptr);
         }
         W.efit[lane] = f;
@@ -271,6 +275,7 @@ __device__ __forceinline__ void init_population_warp(const SolveBuffers& sb, con
     __syncwarp();
 }
 
+template <class S>
 __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_constant__ SolveBuffers sb, int PW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n, P = c_pr.P;
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
                 hdr[j] = sd[j];  // best_ = {seed, cost(seed)}, ik_memetic.cpp:18-22
             }
             double aux[5];
-            const double c = eval_chain(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
+            const double c = eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
             hdr[n] = c;
             hdr[n + 1] = 0.0;
             ProblemMeta m{0, 0, kActive, 0};
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
         if (keep) sb.active[basepos + __popc(mask & ((1u << lane) - 1u))] = (int32_t)b;
     }
     __syncwarp();
-    init_population_warp(sb, W, PW, lane);
+    init_population_warp<S>(sb, W, PW, lane);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -338,6 +343,7 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
 // unperturbed joints), the two line-search points on two lanes, the accepted point on the group leader.
 // Column c holds the GD state of group c.  Returns the number of step() executions of this lane's group.
 // -----------------------------------------------------------------------------------------------
+template <class S>
 __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane, bool valid, const double* g7,
                                              const double* sd, double& best_cost_out) {
     const int n = c_rb.n;
@@ -350,7 +356,7 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
     const double h = c_pr.step_size;
     double local_cost = 0.0, best_cost = 0.0, previous_cost = 0.0;
     int it = 0;
-    if (valid && leader) local_cost = best_cost = eval_chain(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
+    if (valid && leader) local_cost = best_cost = eval_chain<S>(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
     bool act_l = valid && leader && c_pr.gd_max_iters > 0;
     int steps = 0;
     __syncwarp();
@@ -362,7 +368,7 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
             if (act && k < 2 * n) {
                 const int i = k >> 1;
                 const double qi = q[i * kS];
-                W.cs[k * kS + c] = eval_chain(q, nullptr, kViewFd, i, (k & 1) ? qi + h : qi - h, sc, nullptr, g7, sd, nullptr);
+                W.cs[k * kS + c] = eval_chain<S>(q, nullptr, kViewFd, i, (k & 1) ? qi + h : qi - h, sc, nullptr, g7, sd, nullptr);
             }
         }
         __syncwarp();
@@ -373,15 +379,15 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
                 g[i * kS] = gi;
                 sum = sum + fabs(gi);
             }
-            normalise_gradient(g, sum);
+            normalise_gradient<S>(g, sum);
         }
         __syncwarp();
         if (act && gl < 2 && gl < L)
-            W.cs[gl * kS + c] = eval_chain(q, g, gl == 0 ? kViewMinus : kViewPlus, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
+            W.cs[gl * kS + c] = eval_chain<S>(q, g, gl == 0 ? kViewMinus : kViewPlus, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
         __syncwarp();
         if (act && leader) {
-            accept_step(q, g, W.cs[c], W.cs[kS + c]);
-            local_cost = eval_chain(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
+            accept_step<S>(q, g, W.cs[c], W.cs[kS + c]);
+            local_cost = eval_chain<S>(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
             if (local_cost < best_cost) {
                 for (int j = 0; j < n; ++j) best[j * kS] = q[j * kS];
                 best_cost = local_cost;
@@ -404,6 +410,7 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
 // -----------------------------------------------------------------------------------------------
 // One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for PW problems per warp.
 // -----------------------------------------------------------------------------------------------
+template <class S>
 __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
                                                                       int list_in, int L, int PW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -458,11 +465,11 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
             if (valid) {
                 GdState st{W.q + c, W.g + c, W.best + c, W.sc + c, 0.0, 0.0};
                 const double* g7 = W.goal + 7 * k;
-                st.local_cost = st.best_cost = eval_chain(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, nullptr);
+                st.local_cost = st.best_cost = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, nullptr);
                 int it = 0;
                 double previous_cost = 0.0;
                 while (it < c_pr.gd_max_iters) {
-                    gd_step(st, g7, sd, nullptr);
+                    gd_step<S>(st, g7, sd, nullptr);
                     ++gd_steps;
                     if (fabs(st.local_cost - previous_cost) <= c_pr.min_cost_delta) break;
                     previous_cost = st.local_cost;
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
                 best_cost = st.best_cost;
             }
         } else {
-            const int steps = gd_elite_wide(W, L, lane, valid, W.goal + 7 * (valid ? k : 0), sd, best_cost);
+            const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + 7 * (valid ? k : 0), sd, best_cost);
             if (leader) gd_steps = steps;
         }
         // genes <- best, fitness <- cost_fn(best) (== best_cost: same genes, deterministic cost),
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
                         dst[(size_t)(n + j) * P + slot] = 0.0;
                     }
                 }
-                f = eval_chain(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
+                f = eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
                 dst[(size_t)(2 * n) * P + slot] = f;
                 if (ps > 0) removes = f < W.efit[c0 + ia] || f < W.efit[c0 + ib];
             }
@@ -704,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
                 double* col = W.q + lane;
                 for (int j = 0; j < n; ++j) col[j * kS] = hdr[j];
                 double aux[5];
-                eval_chain(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k, sd, aux);
+                eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k, sd, aux);
                 s = solution_from_aux(aux);
             }
             bool done = false, found = false;
@@ -754,7 +761,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
         }
     }
     __syncwarp();
-    init_population_warp(sb, W, PW, lane);
+    init_population_warp<S>(sb, W, PW, lane);
 }
 
 __global__ void fp64_peak_kernel(double* sink, int iters) {
@@ -791,14 +798,43 @@ MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
 
 size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 7) * kS * sizeof(double); }
 
+// Compiled chain signatures (see StaticSpec).  kinds nibble: X 0, Y 1, Z 2, general 3, prismatic 4.
+using SpecAllZ7 = StaticSpec<7, 0x2222222ull, true>;      // Franka Panda and every 7-joint all-z (DH-style) arm + tool frame
+using SpecUr6 = StaticSpec<6, 0x121112ull, true>;         // UR-family: z y y y z y + tool frame
+using SpecFetch8 = StaticSpec<8, 0x01010124ull, true>;    // Fetch arm_with_torso: prismatic z, z y x y x y x + gripper frame
+
+int select_spec(const DevRobot& rb) {
+    static const bool generic_only = std::getenv("PIK_GENERIC_ONLY") != nullptr;
+    if (generic_only) return kSpecGeneric;
+    unsigned long long kinds = 0;
+    for (int j = 0; j < rb.n; ++j) kinds |= (unsigned long long)(rb.kind[j] & 15) << (4 * j);
+    if (rb.n == SpecAllZ7::n && kinds == SpecAllZ7::kinds && rb.has_tip) return kSpecAllZ7;
+    if (rb.n == SpecUr6::n && kinds == SpecUr6::kinds && rb.has_tip) return kSpecUr6;
+    if (rb.n == SpecFetch8::n && kinds == SpecFetch8::kinds && rb.has_tip) return kSpecFetch8;
+    return kSpecGeneric;
+}
+
+#define PIK_DISPATCH_SPEC(spec, CALL)                  \
+    switch (spec) {                                    \
+        case kSpecAllZ7: { using S = SpecAllZ7; CALL; break; }   \
+        case kSpecUr6: { using S = SpecUr6; CALL; break; }       \
+        case kSpecFetch8: { using S = SpecFetch8; CALL; break; } \
+        default: { using S = GenericSpec; CALL; break; }         \
+    }
+
+template <class S>
+static cudaError_t configure_spec() {
+    cudaError_t e = cudaFuncSetAttribute(memetic_generation_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(memetic_init_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gd_local_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
 cudaError_t configure_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(memetic_generation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(memetic_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(eval_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gd_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(eval_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (int spec = 0; spec < kSpecCount && e == cudaSuccess; ++spec) PIK_DISPATCH_SPEC(spec, e = configure_spec<S>());
+    return e;
 }
 
 cudaError_t upload_constants(cudaStream_t stream, const DevRobot& robot, const DevParams& pr) {
@@ -817,29 +853,30 @@ cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double
     return cudaGetLastError();
 }
 
-cudaError_t launch_gd_local(cudaStream_t stream, int n, const SolveBuffers& sb) {
+cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb) {
     if (sb.B <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((sb.B + kThreads - 1) / kThreads);
-    gd_local_kernel<<<blocks, kThreads, gd_local_smem_bytes(n), stream>>>(sb);
+    PIK_DISPATCH_SPEC(spec, (gd_local_kernel<S><<<blocks, kThreads, gd_local_smem_bytes(n), stream>>>(sb)));
     return cudaGetLastError();
 }
 
-cudaError_t launch_memetic_init(cudaStream_t stream, int n, int P, int E, const SolveBuffers& sb) {
+cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb) {
     if (sb.B <= 0) return cudaSuccess;
     const MemeticShape s = memetic_shape(n, P, E, 1);
     const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
     const unsigned blocks = (unsigned)((sb.B + per_block - 1) / per_block);
-    memetic_init_kernel<<<blocks, s.threads, s.smem, stream>>>(sb, s.problems_per_warp);
+    PIK_DISPATCH_SPEC(spec, (memetic_init_kernel<S><<<blocks, s.threads, s.smem, stream>>>(sb, s.problems_per_warp)));
     return cudaGetLastError();
 }
 
-cudaError_t launch_memetic_generation(cudaStream_t stream, int n, int P, int E, const SolveBuffers& sb, int list_in,
-                                      int64_t n_active, int lanes_per_elite) {
+cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb,
+                                      int list_in, int64_t n_active, int lanes_per_elite) {
     if (n_active <= 0) return cudaSuccess;
     const MemeticShape s = memetic_shape(n, P, E, lanes_per_elite);
     const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
     const unsigned blocks = (unsigned)((n_active + per_block - 1) / per_block);
-    memetic_generation_kernel<<<blocks, s.threads, s.smem, stream>>>(sb, list_in, s.lanes_per_elite, s.problems_per_warp);
+    PIK_DISPATCH_SPEC(spec, (memetic_generation_kernel<S><<<blocks, s.threads, s.smem, stream>>>(
+                                sb, list_in, s.lanes_per_elite, s.problems_per_warp)));
     return cudaGetLastError();
 }
 
