@@ -799,33 +799,45 @@ MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
 size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 7) * kS * sizeof(double); }
 
 // Compiled chain signatures (see StaticSpec).  kinds nibble: X 0, Y 1, Z 2, general 3, prismatic 4.
-using SpecAllZ7 = StaticSpec<7, 0x2222222ull, true>;      // Franka Panda and every 7-joint all-z (DH-style) arm + tool frame
-using SpecUr6 = StaticSpec<6, 0x121112ull, true>;         // UR-family: z y y y z y + tool frame
-using SpecFetch8 = StaticSpec<8, 0x01010124ull, true>;    // Fetch arm_with_torso: prismatic z, z y x y x y x + gripper frame
+// Each signature is compiled in two flavours: T (throughput-mode launches, gd_local, init) and L (latency-mode
+// launches of the generation kernel, fully unrolled).
+constexpr unsigned long long kKindsAllZ7 = 0x2222222ull;   // Franka Panda and every 7-joint all-z (DH-style) arm + tool frame
+constexpr unsigned long long kKindsUr6 = 0x121112ull;      // UR family: z y y y z y + tool frame
+constexpr unsigned long long kKindsFetch8 = 0x01010124ull; // Fetch arm_with_torso: prismatic, z y x y x y x + gripper frame
+using SpecAllZ7T = StaticSpec<7, kKindsAllZ7, true, false>;
+using SpecAllZ7L = StaticSpec<7, kKindsAllZ7, true, true>;
+using SpecUr6T = StaticSpec<6, kKindsUr6, true, false>;
+using SpecUr6L = StaticSpec<6, kKindsUr6, true, true>;
+using SpecFetch8T = StaticSpec<8, kKindsFetch8, true, false>;
+using SpecFetch8L = StaticSpec<8, kKindsFetch8, true, true>;
 
 int select_spec(const DevRobot& rb) {
     static const bool generic_only = std::getenv("PIK_GENERIC_ONLY") != nullptr;
     if (generic_only) return kSpecGeneric;
     unsigned long long kinds = 0;
     for (int j = 0; j < rb.n; ++j) kinds |= (unsigned long long)(rb.kind[j] & 15) << (4 * j);
-    if (rb.n == SpecAllZ7::n && kinds == SpecAllZ7::kinds && rb.has_tip) return kSpecAllZ7;
-    if (rb.n == SpecUr6::n && kinds == SpecUr6::kinds && rb.has_tip) return kSpecUr6;
-    if (rb.n == SpecFetch8::n && kinds == SpecFetch8::kinds && rb.has_tip) return kSpecFetch8;
+    if (rb.n == 7 && kinds == kKindsAllZ7 && rb.has_tip) return kSpecAllZ7;
+    if (rb.n == 6 && kinds == kKindsUr6 && rb.has_tip) return kSpecUr6;
+    if (rb.n == 8 && kinds == kKindsFetch8 && rb.has_tip) return kSpecFetch8;
     return kSpecGeneric;
 }
 
-#define PIK_DISPATCH_SPEC(spec, CALL)                  \
-    switch (spec) {                                    \
-        case kSpecAllZ7: { using S = SpecAllZ7; CALL; break; }   \
-        case kSpecUr6: { using S = SpecUr6; CALL; break; }       \
-        case kSpecFetch8: { using S = SpecFetch8; CALL; break; } \
-        default: { using S = GenericSpec; CALL; break; }         \
+// CALL sees S = the throughput flavour of the signature (latency = false) or the latency flavour
+#define PIK_DISPATCH_SPEC(spec, latency, CALL)                                                        \
+    switch ((spec) * 2 + ((latency) ? 1 : 0)) {                                                        \
+        case kSpecAllZ7 * 2: { using S = SpecAllZ7T; CALL; break; }                                    \
+        case kSpecAllZ7 * 2 + 1: { using S = SpecAllZ7L; CALL; break; }                                \
+        case kSpecUr6 * 2: { using S = SpecUr6T; CALL; break; }                                        \
+        case kSpecUr6 * 2 + 1: { using S = SpecUr6L; CALL; break; }                                    \
+        case kSpecFetch8 * 2: { using S = SpecFetch8T; CALL; break; }                                  \
+        case kSpecFetch8 * 2 + 1: { using S = SpecFetch8L; CALL; break; }                              \
+        default: { using S = GenericSpec; CALL; break; }                                               \
     }
 
 template <class S>
-static cudaError_t configure_spec() {
+static cudaError_t configure_spec(bool latency) {
     cudaError_t e = cudaFuncSetAttribute(memetic_generation_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || latency) return e;
     e = cudaFuncSetAttribute(memetic_init_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(gd_local_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -833,7 +845,10 @@ static cudaError_t configure_spec() {
 
 cudaError_t configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(eval_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    for (int spec = 0; spec < kSpecCount && e == cudaSuccess; ++spec) PIK_DISPATCH_SPEC(spec, e = configure_spec<S>());
+    for (int spec = 0; spec < kSpecCount && e == cudaSuccess; ++spec) {
+        PIK_DISPATCH_SPEC(spec, false, e = configure_spec<S>(false));
+        if (e == cudaSuccess && spec != kSpecGeneric) PIK_DISPATCH_SPEC(spec, true, e = configure_spec<S>(true));
+    }
     return e;
 }
 
@@ -856,7 +871,7 @@ cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double
 cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb) {
     if (sb.B <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((sb.B + kThreads - 1) / kThreads);
-    PIK_DISPATCH_SPEC(spec, (gd_local_kernel<S><<<blocks, kThreads, gd_local_smem_bytes(n), stream>>>(sb)));
+    PIK_DISPATCH_SPEC(spec, false, (gd_local_kernel<S><<<blocks, kThreads, gd_local_smem_bytes(n), stream>>>(sb)));
     return cudaGetLastError();
 }
 
@@ -865,7 +880,7 @@ cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int
     const MemeticShape s = memetic_shape(n, P, E, 1);
     const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
     const unsigned blocks = (unsigned)((sb.B + per_block - 1) / per_block);
-    PIK_DISPATCH_SPEC(spec, (memetic_init_kernel<S><<<blocks, s.threads, s.smem, stream>>>(sb, s.problems_per_warp)));
+    PIK_DISPATCH_SPEC(spec, false, (memetic_init_kernel<S><<<blocks, s.threads, s.smem, stream>>>(sb, s.problems_per_warp)));
     return cudaGetLastError();
 }
 
@@ -875,7 +890,7 @@ cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int 
     const MemeticShape s = memetic_shape(n, P, E, lanes_per_elite);
     const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
     const unsigned blocks = (unsigned)((n_active + per_block - 1) / per_block);
-    PIK_DISPATCH_SPEC(spec, (memetic_generation_kernel<S><<<blocks, s.threads, s.smem, stream>>>(
+    PIK_DISPATCH_SPEC(spec, s.lanes_per_elite > 1, (memetic_generation_kernel<S><<<blocks, s.threads, s.smem, stream>>>(
                                 sb, list_in, s.lanes_per_elite, s.problems_per_warp)));
     return cudaGetLastError();
 }
