@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/pik.h"
@@ -127,6 +128,11 @@ inline DevParams make_dev_params(const pik_params& p) {
     d.max_generations = p.memetic_max_generations;
     d.seed_lo = static_cast<uint32_t>(p.rng_seed);
     d.seed_hi = static_cast<uint32_t>(p.rng_seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        d.round_key[2 * r] = d.seed_lo + 0x9E3779B9u * static_cast<uint32_t>(r);
+        d.round_key[2 * r + 1] = d.seed_hi + 0xBB67AE85u * static_cast<uint32_t>(r);
+    }
+    d.debug = std::getenv("PIK_DEBUG_PHASES") ? 1 : 0;
     return d;
 }
 

@@ -22,6 +22,7 @@
 #include "pik_kernels.cuh"
 
 #include <limits.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <cstdlib>
 
@@ -363,12 +364,24 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
     for (;;) {
         const bool act = __shfl_sync(kFull, act_l ? 1 : 0, c * L) != 0 && valid;
         if (!__any_sync(kFull, act)) break;
-        for (int r = 0; r * L < 2 * n; ++r) {
-            const int k = r * L + gl;
-            if (act && k < 2 * n) {
-                const int i = k >> 1;
-                const double qi = q[i * kS];
-                W.cs[k * kS + c] = eval_chain<S>(q, nullptr, kViewFd, i, (k & 1) ? qi + h : qi - h, sc, nullptr, g7, sd, nullptr);
+        if (n <= L) {
+            // one round: lane gl < n walks the finite-difference PAIR of joint gl as two frames in lockstep
+            if (act && gl < n) {
+                Frame A0;
+                frame_load_origin(A0, 0);
+                double cM, cP;
+                gd_pair<S, false>(gl, false, A0, q, nullptr, sc, g7, sd, cM, cP);
+                W.cs[(2 * gl) * kS + c] = cM;
+                W.cs[(2 * gl + 1) * kS + c] = cP;
+            }
+        } else {
+            for (int r = 0; r * L < 2 * n; ++r) {
+                const int k = r * L + gl;
+                if (act && k < 2 * n) {
+                    const int i = k >> 1;
+                    const double qi = q[i * kS];
+                    W.cs[k * kS + c] = eval_chain<S>(q, nullptr, kViewFd, i, (k & 1) ? qi + h : qi - h, sc, nullptr, g7, sd, nullptr);
+                }
             }
         }
         __syncwarp();
@@ -432,6 +445,9 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
     }
     __syncwarp();
 
+    const bool dbg = c_pr.debug && blockIdx.x == 0 && warp == 0 && lane == 0;
+    long long t_start = 0, t_gd = 0, t_rep = 0, t_sort = 0, t_book = 0;
+    if (dbg) t_start = clock64();
     // ---- gradientDescent(i) for every elite (src/ik_memetic.cpp:66-91, 230-239)
     int gd_steps = 0;
     {
@@ -497,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
     }
     __syncwarp();
 
+    if (dbg) t_gd = clock64();
     // ---- per problem: reproduce, sortPopulation, best update
     const double inv_n = 1.0 / (double)n;
     int n_problems = 0;
@@ -525,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
         // child), so its draws do not depend on the history.
         int s = E;
         double* col = W.q + lane;
+        if (dbg) t_rep -= clock64();
         while (s < P) {
             const int i = s + lane;
             const bool actv = i < P;
@@ -618,6 +636,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
             __syncwarp();
         }
 
+        if (dbg) t_rep += clock64();
         // sortPopulation (src/ik_memetic.cpp:200-209) under the total order (fitness, position), NaN last.
         if (c_rb.any_unbounded) {
             // whole order needed: the previous occupant of every position may seed a random individual
@@ -693,6 +712,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
         __syncwarp();
     }
 
+    if (dbg) t_sort = clock64();
     // ---- per problem, one lane each: solution test, wipeout check, bookkeeping
     {
         bool keep = false;
@@ -761,7 +781,11 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
         }
     }
     __syncwarp();
+    if (dbg) t_book = clock64();
     init_population_warp<S>(sb, W, PW, lane);
+    if (dbg)
+        printf("pik phases L=%d PW=%d: gd %lld  reproduce %lld  sort+best %lld  bookkeeping %lld  init %lld cycles (gd steps %d)\n", L,
+               PW, t_gd - t_start, t_rep, t_sort - t_gd - t_rep, t_book - t_sort, clock64() - t_book, gd_steps);
 }
 
 __global__ void fp64_peak_kernel(double* sink, int iters) {

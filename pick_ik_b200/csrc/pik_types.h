@@ -41,6 +41,9 @@ struct DevParams {
     int stop_on_valid, approx;
     int P, E, max_generations;
     uint32_t seed_lo, seed_hi;
+    uint32_t round_key[20];  // Philox4x32-10 key schedule of (seed_lo, seed_hi): k0_r, k1_r for round r
+    int debug;  // PIK_DEBUG_PHASES: warp 0 of CTA 0 prints the cycle count of each phase of a generation
+    int pad_;
 };
 
 // status codes in meta[b].status
