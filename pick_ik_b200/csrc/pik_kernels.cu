@@ -32,11 +32,8 @@ namespace pik {
 
 namespace {
 
-#ifndef PIK_GEN_MIN_BLOCKS
-#define PIK_GEN_MIN_BLOCKS 3
-#endif
-
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 4;       // every kernel but the throughput-mode generation launches
+constexpr int kWarpsPerBlockBulk = 8;   // throughput-mode generation launches: 8 warps in step (see `lockstep`)
 constexpr int kThreads = 32 * kWarpsPerBlock;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -423,15 +420,27 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
 // -----------------------------------------------------------------------------------------------
 // One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for PW problems per warp.
 // -----------------------------------------------------------------------------------------------
+// Register budgets: the latency flavour runs 3 CTAs of 4 warps per SM at 168 registers; the throughput flavour (and
+// the generic kernel, which serves both modes) 2 CTAs of 8 warps at 128.
 template <class S>
-__global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
+__global__ void __launch_bounds__(S::kUnroll ? 128 : 256, S::kUnroll ? 3 : 2) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
                                                                       int list_in, int L, int PW) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_active = sb.counters[list_in];
-    const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * PW;
-    if (base >= n_active) return;
+    const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * PW;
+    // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
+    // GD step (below): warps that run the same code at the same time share their instruction-cache fills,
+    // and instruction fetch is what bounds this kernel (ncu: gcc instruction requests at 94 % of peak).
+    const bool lockstep = L == 1 && c_pr.lockstep != 0;
+    if (base >= n_active) {
+        if (lockstep) {
+            for (int step = 0; step < c_pr.gd_max_iters; ++step) __syncthreads();
+            for (int k = 0; k < PW; ++k) __syncthreads();
+        }
+        return;
+    }
     const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, PW), n, P, PW);
     const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;
     int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
@@ -478,21 +487,25 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
         __syncwarp();
         double best_cost = 0.0;
         if (L == 1) {
-            if (valid) {
-                GdState st{W.q + c, W.g + c, W.best + c, W.sc + c, 0.0, 0.0};
-                const double* g7 = W.goal + 7 * k;
-                st.local_cost = st.best_cost = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, nullptr);
-                int it = 0;
-                double previous_cost = 0.0;
-                while (it < c_pr.gd_max_iters) {
+            GdState st{W.q + c, W.g + c, W.best + c, W.sc + c, 0.0, 0.0};
+            const double* g7 = W.goal + 7 * (valid ? k : 0);
+            if (valid) st.local_cost = st.best_cost = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, nullptr);
+            bool going = valid;
+            double previous_cost = 0.0;
+            for (int step = 0; step < c_pr.gd_max_iters; ++step) {
+                if (lockstep) {
+                    __syncthreads();
+                } else if (!__any_sync(kFull, going)) {
+                    break;
+                }
+                if (going) {
                     gd_step<S>(st, g7, sd, nullptr);
                     ++gd_steps;
-                    if (fabs(st.local_cost - previous_cost) <= c_pr.min_cost_delta) break;
+                    if (fabs(st.local_cost - previous_cost) <= c_pr.min_cost_delta) going = false;
                     previous_cost = st.local_cost;
-                    ++it;
                 }
-                best_cost = st.best_cost;
             }
+            best_cost = st.best_cost;
         } else {
             const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + 7 * (valid ? k : 0), sd, best_cost);
             if (leader) gd_steps = steps;
@@ -518,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, PIK_GEN_MIN_BLOCKS) memetic_generati
     const double inv_n = 1.0 / (double)n;
     int n_problems = 0;
     for (int k = 0; k < PW; ++k) {
+        if (lockstep) __syncthreads();  // re-align the CTA's warps at every problem (instruction-cache sharing)
         const int b = W.pidx[k];
         if (b < 0) continue;
         ++n_problems;
@@ -810,13 +824,15 @@ int memetic_max_lanes_per_elite(int E) {
 
 MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
     MemeticShape s;
-    s.threads = kThreads;
-    s.warps = kWarpsPerBlock;
     int L = lanes_per_elite < 1 ? 1 : lanes_per_elite;
     if (L > memetic_max_lanes_per_elite(E)) L = memetic_max_lanes_per_elite(E);
     s.lanes_per_elite = L;
     s.problems_per_warp = 32 / (E * L);
-    s.smem = kWarpsPerBlock * warp_smem_bytes(n, P, s.problems_per_warp);
+    s.warps = L == 1 ? kWarpsPerBlockBulk : kWarpsPerBlock;
+    // a large population may not leave room for 8 warps' worth of shared memory
+    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, s.problems_per_warp) > 110 * 1024) s.warps >>= 1;
+    s.threads = 32 * s.warps;
+    s.smem = s.warps * warp_smem_bytes(n, P, s.problems_per_warp);
     return s;
 }
 
@@ -901,7 +917,10 @@ cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuf
 
 cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb) {
     if (sb.B <= 0) return cudaSuccess;
-    const MemeticShape s = memetic_shape(n, P, E, 1);
+    MemeticShape s = memetic_shape(n, P, E, 1);
+    s.warps = kWarpsPerBlock;
+    s.threads = kThreads;
+    s.smem = s.warps * warp_smem_bytes(n, P, s.problems_per_warp);
     const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
     const unsigned blocks = (unsigned)((sb.B + per_block - 1) / per_block);
     PIK_DISPATCH_SPEC(spec, false, (memetic_init_kernel<S><<<blocks, s.threads, s.smem, stream>>>(sb, s.problems_per_warp)));

@@ -42,8 +42,8 @@ struct DevParams {
     int P, E, max_generations;
     uint32_t seed_lo, seed_hi;
     uint32_t round_key[20];  // Philox4x32-10 key schedule of (seed_lo, seed_hi): k0_r, k1_r for round r
+    int lockstep;  // block barrier per GD step in throughput mode (PIK_NO_LOCKSTEP disables)
     int debug;  // PIK_DEBUG_PHASES: warp 0 of CTA 0 prints the cycle count of each phase of a generation
-    int pad_;
 };
 
 // status codes in meta[b].status
