@@ -90,15 +90,20 @@ bool trace_enabled() {
     return v;
 }
 
-// Lanes per elite for a generation over n_active problems: the largest power of two (up to the warp's
-// capacity) that still lets every problem's warps be resident at once -- below that point the batch is
-// latency-bound and spreading one GD step over more lanes is free; above it lanes are better spent on
-// whole GD instances (throughput mode, 1 lane per elite).
+// PIK_TRACE_GENERATIONS: one launch per generation even in wide mode (per-generation timing)
+bool trace_each_generation() { return std::getenv("PIK_TRACE_GENERATIONS") != nullptr; }
+
+// Lanes per elite for a generation over n_active problems.  A lone warp of this code issues ~0.2
+// instructions per cycle (dependent FP64 chains: 8-cycle DFMA latency), so an SM sub-partition needs 4-5
+// resident warps to stay busy and a launch with fewer is latency-bound.  Throughput mode (1 lane per elite: a
+// whole GD instance per lane, 32 / E problems per warp) executes the fewest instructions per problem but has
+// the longest serial path per generation; as the batch drains, the warp's lanes are spread over the
+// evaluations of each GD step instead (L lanes per elite): the largest L that still keeps about
+// `warps_per_sm` warps per SM.  PIK_WIDE_WARPS_PER_SM overrides the target (read per call: the parity tests
+// run both mappings; 0 = always throughput mode, huge = always the widest mapping).
 int lanes_for(int64_t n_active, int E, int sm_count) {
-    static const int64_t warps_per_sm = [] {
-        const char* e = std::getenv("PIK_WIDE_WARPS_PER_SM");
-        return e ? std::atoll(e) : (int64_t)12;
-    }();
+    const char* env = std::getenv("PIK_WIDE_WARPS_PER_SM");
+    const int64_t warps_per_sm = env ? std::atoll(env) : (int64_t)16;
     const int64_t capacity_lanes = (int64_t)sm_count * warps_per_sm * 32;
     const int lmax = memetic_max_lanes_per_elite(E);
     int L = 1;
@@ -386,7 +391,13 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
             PIK_CUDA(s, cudaMemsetAsync(sb.counters + (list ^ 1), 0, sizeof(int32_t), st));
             PIK_CUDA(s, cudaEventRecord(s->ev2, st));
             const int lanes = lanes_for(n_active, pr.E, s->sm_count);
-            PIK_CUDA(s, launch_memetic_generation(st, s->spec, n, P, pr.E, sb, list, n_active, lanes));
+            // a launch with one problem per warp runs every remaining generation of its problems
+            // (only once every warp has an SM sub-partition to itself: a launch per generation re-spreads the
+            // survivors over the SMs, a persistent warp stays where it started)
+            const bool persistent = memetic_shape(n, P, pr.E, lanes).problems_per_warp == 1 &&
+                                    n_active <= (int64_t)s->sm_count * 4 && !trace_each_generation();
+            const int max_gens = persistent ? pr.max_generations - gen : 1;
+            PIK_CUDA(s, launch_memetic_generation(st, s->spec, n, P, pr.E, sb, list, n_active, lanes, max_gens));
             PIK_CUDA(s, cudaEventRecord(s->ev3, st));
             s->stats.kernel_launches += 1;
             s->stats.generation_launches += 1;

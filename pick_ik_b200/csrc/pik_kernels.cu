@@ -336,10 +336,17 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
 }
 
 // -----------------------------------------------------------------------------------------------
-// gradientDescent(i) (src/ik_memetic.cpp:66-91) with L lanes per elite: the 2n finite-difference
-// evaluations of a step run on different lanes (each a full chain walk with the cached sin/cos of the
-// unperturbed joints), the two line-search points on two lanes, the accepted point on the group leader.
+// gradientDescent(i) (src/ik_memetic.cpp:66-91) with L lanes per elite.  A GD step is two rounds of
+// single-frame evaluations, every one through the same eval_chain call site:
+//   round A   the 2n finite-difference points of the current configuration AND the current configuration
+//             itself (2n + 1 tasks spread over the L lanes of the group), all reading the sin/cos cache the
+//             group filled cooperatively just before (one joint per lane).  Evaluating the accepted point
+//             of step s together with the finite differences of step s + 1 removes a whole serial
+//             evaluation from every step; the finite differences are speculative (discarded if the
+//             termination test of step s fires).
+//   round B   the two line-search points on two lanes.
 // Column c holds the GD state of group c.  Returns the number of step() executions of this lane's group.
+// Results are bit-identical to the serial loop: every evaluation is a full chain walk of its configuration.
 // -----------------------------------------------------------------------------------------------
 template <class S>
 __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane, bool valid, const double* g7,
@@ -352,64 +359,92 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
     double* best = W.best + c;
     double* sc = W.sc + c;
     const double h = c_pr.step_size;
+    const int acc_lane = c * L + n % L;  // lane that evaluates the current configuration
     double local_cost = 0.0, best_cost = 0.0, previous_cost = 0.0;
-    int it = 0;
-    if (valid && leader) local_cost = best_cost = eval_chain<S>(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
-    bool act_l = valid && leader && c_pr.gd_max_iters > 0;
-    int steps = 0;
-    __syncwarp();
+    int it = 0, steps = 0;
+    bool act_l = valid && leader;  // the group still runs (leader's copy)
+    bool first = true;
     for (;;) {
         const bool act = __shfl_sync(kFull, act_l ? 1 : 0, c * L) != 0 && valid;
         if (!__any_sync(kFull, act)) break;
-        if (n <= L) {
-            // one round: lane gl < n walks the finite-difference PAIR of joint gl as two frames in lockstep
-            if (act && gl < n) {
-                Frame A0;
-                frame_load_origin(A0, 0);
-                double cM, cP;
-                gd_pair<S, false>(gl, false, A0, q, nullptr, sc, g7, sd, cM, cP);
-                W.cs[(2 * gl) * kS + c] = cM;
-                W.cs[(2 * gl + 1) * kS + c] = cP;
+        // sin/cos cache of the current configuration, one joint per lane
+        for (int j = gl; j < n; j += L) {
+            if (act) {
+                double sj, cj;
+                joint_sincos<S>(j, q[j * kS], sj, cj);
+                sc[(2 * j) * kS] = sj;
+                sc[(2 * j + 1) * kS] = cj;
             }
-        } else {
-            for (int r = 0; r * L < 2 * n; ++r) {
-                const int k = r * L + gl;
-                if (act && k < 2 * n) {
-                    const int i = k >> 1;
-                    const double qi = q[i * kS];
-                    W.cs[k * kS + c] = eval_chain<S>(q, nullptr, kViewFd, i, (k & 1) ? qi + h : qi - h, sc, nullptr, g7, sd, nullptr);
+        }
+        __syncwarp();
+        // round A: n finite-difference pairs + the current configuration, one task per lane and sub-round
+        double cur = 0.0;
+        for (int k = gl; k <= n; k += L) {
+            if (act) {
+                const CostPair cp = pair_costs_from_origin<S>(kPairFd, k < n ? k : -1, q, nullptr, sc, g7, sd);
+                if (k < n) {
+                    W.cs[(2 * k) * kS + c] = cp.m;
+                    W.cs[(2 * k + 1) * kS + c] = cp.p;
+                } else {
+                    cur = cp.m;
                 }
             }
         }
+        cur = __shfl_sync(kFull, cur, acc_lane);
         __syncwarp();
+        bool improved = false;
         if (act && leader) {
-            double sum = h;
-            for (int i = 0; i < n; ++i) {
-                const double gi = W.cs[(2 * i + 1) * kS + c] - W.cs[(2 * i) * kS + c];
-                g[i * kS] = gi;
-                sum = sum + fabs(gi);
+            if (first) {
+                local_cost = best_cost = cur;  // GradientIk::from
+                if (c_pr.gd_max_iters <= 0) act_l = false;
+            } else {
+                // the tail of step(): the accepted point's cost, best update (ik_gradient.cpp:88-93), then the
+                // loop control of gradientDescent (ik_memetic.cpp:75-86)
+                local_cost = cur;
+                if (local_cost < best_cost) {
+                    improved = true;
+                    best_cost = local_cost;
+                }
+                ++steps;
+                if (fabs(local_cost - previous_cost) <= c_pr.min_cost_delta) {
+                    act_l = false;
+                } else {
+                    previous_cost = local_cost;
+                    ++it;
+                    if (it >= c_pr.gd_max_iters) act_l = false;
+                }
             }
-            normalise_gradient<S>(g, sum);
+        }
+        first = false;
+        const unsigned ctl = __shfl_sync(kFull, (act_l ? 1u : 0u) | (improved ? 2u : 0u), c * L);
+        const bool go = (ctl & 1u) != 0 && valid;
+        // one joint per lane: best <- local when improved; the gradient g_i = C(q + h e_i) - C(q - h e_i), its
+        // normalisation by h / (h + sum |g_i|) (ik_gradient.cpp:42-54; the sum runs in joint order on every lane)
+        if (act) {
+            double f = 0.0;
+            if (go) {
+                double sum = h;
+                for (int i = 0; i < n; ++i) sum = sum + fabs(W.cs[(2 * i + 1) * kS + c] - W.cs[(2 * i) * kS + c]);
+                f = 1.0 / sum * h;
+            }
+            for (int j = gl; j < n; j += L) {
+                if (ctl & 2u) best[j * kS] = q[j * kS];
+                if (go) g[j * kS] = (W.cs[(2 * j + 1) * kS + c] - W.cs[(2 * j) * kS + c]) * f;
+            }
         }
         __syncwarp();
-        if (act && gl < 2 && gl < L)
+        // round B: the line search
+        if (go && gl < 2)
             W.cs[gl * kS + c] = eval_chain<S>(q, g, gl == 0 ? kViewMinus : kViewPlus, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
         __syncwarp();
-        if (act && leader) {
-            accept_step<S>(q, g, W.cs[c], W.cs[kS + c]);
-            local_cost = eval_chain<S>(q, nullptr, kViewPlain, -1, 0.0, nullptr, sc, g7, sd, nullptr);
-            if (local_cost < best_cost) {
-                for (int j = 0; j < n; ++j) best[j * kS] = q[j * kS];
-                best_cost = local_cost;
-            }
-            ++steps;
-            if (fabs(local_cost - previous_cost) <= c_pr.min_cost_delta) {
-                act_l = false;
-            } else {
-                previous_cost = local_cost;
-                ++it;
-                if (it >= c_pr.gd_max_iters) act_l = false;
-            }
+        // the always-accepted step (ik_gradient.cpp:67-85), one joint per lane
+        if (go) {
+            const double p1 = W.cs[c], p3 = W.cs[kS + c];
+            const double p2 = (p1 + p3) * 0.5;
+            const double cost_diff = (p3 - p1) * 0.5;
+            double joint_diff = p2 / cost_diff;
+            if (!(fabs(joint_diff) <= 0x1.fffffffffffffp+1023)) joint_diff = 0.0;  // !isfinite
+            for (int j = gl; j < n; j += L) q[j * kS] = clamp_to_limits(j, q[j * kS] - g[j * kS] * joint_diff);
         }
         __syncwarp();
     }
@@ -420,19 +455,23 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
 // -----------------------------------------------------------------------------------------------
 // One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for PW problems per warp.
 // -----------------------------------------------------------------------------------------------
-// Register budgets: the latency flavour runs 3 CTAs of 4 warps per SM at 168 registers; the throughput flavour (and
-// the generic kernel, which serves both modes) 2 CTAs of 8 warps at 128.
+// Register budgets: the throughput flavour (and the generic kernel, which serves both modes) runs 2 CTAs of
+// 8 warps per SM at 128 registers; the wide flavour (several lanes per elite) small CTAs of 4 warps.
+//
+// max_gens: generations this launch may run per problem.  Throughput launches run one (the host compacts the
+// active list between launches).  A launch with one problem per warp (PW == 1) may run many: the warp keeps
+// its problem until it is solved, has failed or has used its budget -- problems are independent, so the tail
+// of the batch needs no global step between generations and the hardware block scheduler balances the load.
 template <class S>
-__global__ void __launch_bounds__(S::kUnroll ? 128 : 256, S::kUnroll ? 3 : 2) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
-                                                                      int list_in, int L, int PW) {
+__global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 4 : 2) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
+                                                                      int list_in, int L, int PW, int max_gens) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_active = sb.counters[list_in];
     const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * PW;
     // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
-    // GD step (below): warps that run the same code at the same time share their instruction-cache fills,
-    // and instruction fetch is what bounds this kernel (ncu: gcc instruction requests at 94 % of peak).
+    // GD step (below): warps that run the same code at the same time share their instruction-cache fills.
     const bool lockstep = L == 1 && c_pr.lockstep != 0;
     if (base >= n_active) {
         if (lockstep) {
@@ -444,7 +483,6 @@ __global__ void __launch_bounds__(S::kUnroll ? 128 : 256, S::kUnroll ? 3 : 2) me
     const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, PW), n, P, PW);
     const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;
     int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
-
     if (lane < PW) {
         const int64_t idx = base + lane;
         const int b = idx < n_active ? act_in[idx] : -1;
@@ -454,6 +492,7 @@ __global__ void __launch_bounds__(S::kUnroll ? 128 : 256, S::kUnroll ? 3 : 2) me
     }
     __syncwarp();
 
+  for (int gen_here = 0;; ++gen_here) {
     const bool dbg = c_pr.debug && blockIdx.x == 0 && warp == 0 && lane == 0;
     long long t_start = 0, t_gd = 0, t_rep = 0, t_sort = 0, t_book = 0;
     if (dbg) t_start = clock64();
@@ -779,11 +818,6 @@ __global__ void __launch_bounds__(S::kUnroll ? 128 : 256, S::kUnroll ? 3 : 2) me
             }
             sb.meta[b] = m;
         }
-        const unsigned mask = __ballot_sync(kFull, keep);
-        int basepos = 0;
-        if (lane == 0 && mask) basepos = atomicAdd(&sb.counters[list_in ^ 1], __popc(mask));
-        basepos = __shfl_sync(kFull, basepos, 0);
-        if (keep) act_out[basepos + __popc(mask & ((1u << lane) - 1u))] = b;
         if (sb.stats) {
             int steps = gd_steps;
 #pragma unroll
@@ -793,13 +827,26 @@ __global__ void __launch_bounds__(S::kUnroll ? 128 : 256, S::kUnroll ? 3 : 2) me
                 atomicAdd(&sb.stats[1], (unsigned long long)steps);
             }
         }
+        const unsigned mask = __ballot_sync(kFull, keep);
+        // the warp keeps its (single) problem for another generation
+        const bool again = PW == 1 && mask != 0 && gen_here + 1 < max_gens;
+        if (!again) {
+            int basepos = 0;
+            if (lane == 0 && mask) basepos = atomicAdd(&sb.counters[list_in ^ 1], __popc(mask));
+            basepos = __shfl_sync(kFull, basepos, 0);
+            if (keep) act_out[basepos + __popc(mask & ((1u << lane) - 1u))] = b;
+        }
+        __syncwarp();
+        if (dbg) t_book = clock64();
+        init_population_warp<S>(sb, W, PW, lane);
+        if (dbg)
+            printf("pik phases L=%d PW=%d: gd %lld  reproduce %lld  sort+best %lld  bookkeeping %lld  init %lld cycles (gd steps %d)\n", L,
+                   PW, t_gd - t_start, t_rep, t_sort - t_gd - t_rep, t_book - t_sort, clock64() - t_book, gd_steps);
+        if (!again) break;
+        if (lane < PW) W.flag[lane] = 0;
+        __syncwarp();
     }
-    __syncwarp();
-    if (dbg) t_book = clock64();
-    init_population_warp<S>(sb, W, PW, lane);
-    if (dbg)
-        printf("pik phases L=%d PW=%d: gd %lld  reproduce %lld  sort+best %lld  bookkeeping %lld  init %lld cycles (gd steps %d)\n", L,
-               PW, t_gd - t_start, t_rep, t_sort - t_gd - t_rep, t_book - t_sort, clock64() - t_book, gd_steps);
+  }
 }
 
 __global__ void fp64_peak_kernel(double* sink, int iters) {
@@ -839,17 +886,14 @@ MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
 size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 7) * kS * sizeof(double); }
 
 // Compiled chain signatures (see StaticSpec).  kinds nibble: X 0, Y 1, Z 2, general 3, prismatic 4.
-// Each signature is compiled in two flavours: T (throughput-mode launches, gd_local, init) and L (latency-mode
-// launches of the generation kernel, fully unrolled).
-constexpr unsigned long long kKindsAllZ7 = 0x2222222ull;   // Franka Panda and every 7-joint all-z (DH-style) arm + tool frame
-constexpr unsigned long long kKindsUr6 = 0x121112ull;      // UR family: z y y y z y + tool frame
-constexpr unsigned long long kKindsFetch8 = 0x01010124ull; // Fetch arm_with_torso: prismatic, z y x y x y x + gripper frame
+// Every signature is compiled in two flavours: throughput (generation launches with one lane per elite,
+// gd_local, init) and wide (generation launches with several lanes per elite).
+constexpr unsigned long long kKindsAllZ7 = 0x2222222ull;  // Franka Panda and every 7-joint all-z (DH-style) arm + tool frame
 using SpecAllZ7T = StaticSpec<7, kKindsAllZ7, true, false>;
-using SpecAllZ7L = StaticSpec<7, kKindsAllZ7, true, true>;
-using SpecUr6T = StaticSpec<6, kKindsUr6, true, false>;
-using SpecUr6L = StaticSpec<6, kKindsUr6, true, true>;
-using SpecFetch8T = StaticSpec<8, kKindsFetch8, true, false>;
-using SpecFetch8L = StaticSpec<8, kKindsFetch8, true, true>;
+using SpecAllZ7W = StaticSpec<7, kKindsAllZ7, true, true>;
+struct GenericSpecW : GenericSpec {
+    static constexpr bool kWide = true;
+};
 
 int select_spec(const DevRobot& rb) {
     static const bool generic_only = std::getenv("PIK_GENERIC_ONLY") != nullptr;
@@ -857,27 +901,22 @@ int select_spec(const DevRobot& rb) {
     unsigned long long kinds = 0;
     for (int j = 0; j < rb.n; ++j) kinds |= (unsigned long long)(rb.kind[j] & 15) << (4 * j);
     if (rb.n == 7 && kinds == kKindsAllZ7 && rb.has_tip) return kSpecAllZ7;
-    if (rb.n == 6 && kinds == kKindsUr6 && rb.has_tip) return kSpecUr6;
-    if (rb.n == 8 && kinds == kKindsFetch8 && rb.has_tip) return kSpecFetch8;
     return kSpecGeneric;
 }
 
-// CALL sees S = the throughput flavour of the signature (latency = false) or the latency flavour
-#define PIK_DISPATCH_SPEC(spec, latency, CALL)                                                        \
-    switch ((spec) * 2 + ((latency) ? 1 : 0)) {                                                        \
+// CALL sees S = the throughput flavour of the signature (wide = false) or the wide flavour
+#define PIK_DISPATCH_SPEC(spec, wide, CALL)                                                            \
+    switch ((spec) * 2 + ((wide) ? 1 : 0)) {                                                           \
         case kSpecAllZ7 * 2: { using S = SpecAllZ7T; CALL; break; }                                    \
-        case kSpecAllZ7 * 2 + 1: { using S = SpecAllZ7L; CALL; break; }                                \
-        case kSpecUr6 * 2: { using S = SpecUr6T; CALL; break; }                                        \
-        case kSpecUr6 * 2 + 1: { using S = SpecUr6L; CALL; break; }                                    \
-        case kSpecFetch8 * 2: { using S = SpecFetch8T; CALL; break; }                                  \
-        case kSpecFetch8 * 2 + 1: { using S = SpecFetch8L; CALL; break; }                              \
+        case kSpecAllZ7 * 2 + 1: { using S = SpecAllZ7W; CALL; break; }                                \
+        case kSpecGeneric * 2 + 1: { using S = GenericSpecW; CALL; break; }                            \
         default: { using S = GenericSpec; CALL; break; }                                               \
     }
 
 template <class S>
-static cudaError_t configure_spec(bool latency) {
+static cudaError_t configure_spec(bool wide) {
     cudaError_t e = cudaFuncSetAttribute(memetic_generation_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess || latency) return e;
+    if (e != cudaSuccess || wide) return e;
     e = cudaFuncSetAttribute(memetic_init_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(gd_local_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -887,7 +926,7 @@ cudaError_t configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(eval_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     for (int spec = 0; spec < kSpecCount && e == cudaSuccess; ++spec) {
         PIK_DISPATCH_SPEC(spec, false, e = configure_spec<S>(false));
-        if (e == cudaSuccess && spec != kSpecGeneric) PIK_DISPATCH_SPEC(spec, true, e = configure_spec<S>(true));
+        if (e == cudaSuccess) PIK_DISPATCH_SPEC(spec, true, e = configure_spec<S>(true));
     }
     return e;
 }
@@ -928,13 +967,13 @@ cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int
 }
 
 cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb,
-                                      int list_in, int64_t n_active, int lanes_per_elite) {
+                                      int list_in, int64_t n_active, int lanes_per_elite, int max_gens) {
     if (n_active <= 0) return cudaSuccess;
     const MemeticShape s = memetic_shape(n, P, E, lanes_per_elite);
     const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
     const unsigned blocks = (unsigned)((n_active + per_block - 1) / per_block);
     PIK_DISPATCH_SPEC(spec, s.lanes_per_elite > 1, (memetic_generation_kernel<S><<<blocks, s.threads, s.smem, stream>>>(
-                                sb, list_in, s.lanes_per_elite, s.problems_per_warp)));
+                                sb, list_in, s.lanes_per_elite, s.problems_per_warp, max_gens)));
     return cudaGetLastError();
 }
 

@@ -10,8 +10,7 @@ namespace pik {
 
 // Launch shape of the memetic kernels.  Every warp is autonomous: it owns `problems_per_warp` problems
 // and gives each of their E elites `lanes_per_elite` lanes (1 = throughput mode: a whole GD instance per
-// lane; > 1 = latency mode for a nearly drained batch: the finite-difference evaluations of one step run
-// on different lanes).
+// lane; > 1 = wide mode for a draining batch: the evaluations of one GD step run on different lanes).
 struct MemeticShape {
     int threads;            // per CTA
     int warps;              // per CTA
@@ -29,17 +28,18 @@ cudaError_t upload_constants(cudaStream_t stream, const DevRobot& robot, const D
 cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double* goal_pose, const double* seed,
                              int64_t seed_stride, const double* q, double* cost, int32_t* is_solution,
                              double* tip_pose);
-// Chain signatures the kernels are compiled for (straight-line, branch-free chain walks); any other
+// Chain signatures the kernels are compiled for (compile-time n, kind dispatch folded away); any other
 // robot runs the generic kernels.  select_spec() matches a robot table against them.
-enum : int { kSpecGeneric = 0, kSpecAllZ7 = 1, kSpecUr6 = 2, kSpecFetch8 = 3, kSpecCount = 4 };
+enum : int { kSpecGeneric = 0, kSpecAllZ7 = 1, kSpecCount = 2 };
 int select_spec(const DevRobot& robot);
 
 cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb);
 cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb);
-// One launch advances every problem of active list `list_in` by one generation and appends the
-// still-active ones to the other list.  n_active bounds the grid.
+// One launch advances every problem of active list `list_in` by one generation (or, with one problem per
+// warp, by up to max_gens generations) and appends the still-active ones to the other list.  n_active
+// bounds the grid.
 cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb,
-                                      int list_in, int64_t n_active, int lanes_per_elite);
+                                      int list_in, int64_t n_active, int lanes_per_elite, int max_gens);
 // FP64 FMA throughput microbenchmark (roofline denominator for the FP64 bound)
 cudaError_t launch_fp64_peak(cudaStream_t stream, double* sink, int blocks, int threads, int iters);
 cudaError_t configure_kernels();

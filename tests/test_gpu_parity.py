@@ -117,8 +117,14 @@ MEMETIC_CASES = [
 ]
 
 
+@pytest.mark.parametrize("mapping", ["throughput", "wide", "wide-per-generation"])
 @pytest.mark.parametrize("name,kw,B", MEMETIC_CASES)
-def test_memetic_parity(solvers, name, kw, B):
+def test_memetic_parity(solvers, name, kw, B, mapping, monkeypatch):
+    # the two lane mappings of the generation kernel (1 lane per elite / the warp spread over one
+    # problem's GD evaluations, which also keeps a problem for all its generations in one launch)
+    monkeypatch.setenv("PIK_WIDE_WARPS_PER_SM", "0" if mapping == "throughput" else "1000000000")
+    if mapping == "wide-per-generation":
+        monkeypatch.setenv("PIK_TRACE_GENERATIONS", "1")
     chain, orobot, solver = solvers(name)
     op, gp = both_params(mode="global", **kw)
     goal = orc.make_targets(orobot, B)
