@@ -6,7 +6,8 @@ memetic solver (population 128, 4 elites, 25 GD iterations per elite, <= 100 gen
 Panda home.  `value` times device-resident inputs -> device-resident outputs with CUDA events; `e2e` times
 the same call through the C-ABI with pinned HOST buffers (H2D and D2H inside).  N > 1 (torchrun): one
 process per GPU, weak scaling (each rank its own 65 536 poses, RNG keyed by the global problem index), one
-NCCL all-gather of the packed solutions inside the timed region, max over ranks.
+NCCL all-gather of the packed solutions inside the timed region (pik_solve_batch_sharded: the library's own
+communicator, torch.distributed only carries the unique id and the barriers), max over ranks.
 
 `--impl reference` times the reference's CPU algorithm (oracle/pik_oracle.c, a restatement: the reference
 itself needs ROS 2 / MoveIt / Eigen and cannot be built here) on all host cores on a bounded sample.
@@ -225,13 +226,21 @@ def run_ours(args):
     d_cost = torch.empty(B, dtype=torch.float64, device=dev)
     d_its = torch.empty(B, dtype=torch.int32, device=dev)
     gathered = torch.empty((world, B, n + 3), dtype=torch.float64, device=dev) if world > 1 else None
+    comm = None
+    if world > 1:
+        # the library's own NCCL communicator: rank 0 draws the id, torch.distributed only carries the bytes
+        ids = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = capi.Comm(ids[0], world, rank, local_rank)
 
     def step_device():
-        solver.solve_batch_ptr(params, B, first, d_goal.data_ptr(), d_seed.data_ptr(), 0, d_sol.data_ptr(),
-                               d_err.data_ptr(), d_cost.data_ptr(), d_its.data_ptr(), capi.MEM_DEVICE)
-        if world > 1:
-            packed = torch.cat([d_sol, d_cost[:, None], d_err.double()[:, None], d_its.double()[:, None]], dim=1)
-            dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+        if world == 1:
+            solver.solve_batch_ptr(params, B, first, d_goal.data_ptr(), d_seed.data_ptr(), 0, d_sol.data_ptr(),
+                                   d_err.data_ptr(), d_cost.data_ptr(), d_its.data_ptr(), capi.MEM_DEVICE)
+        else:
+            # shard solve + ncclAllGather of the packed results on the solver's stream (pik_solve_batch_sharded)
+            solver.solve_batch_sharded_ptr(comm, params, B, first, d_goal.data_ptr(), d_seed.data_ptr(), 0,
+                                           gathered.data_ptr(), capi.MEM_DEVICE)
 
     def barrier():
         if world > 1:
@@ -271,7 +280,10 @@ def run_ours(args):
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
-    solved = int((d_err == 1).sum().item())
+    if world == 1:
+        solved = int((d_err == 1).sum().item())
+    else:
+        solved = int((gathered[rank, :, n + 1] == 1).sum().item())
 
     # ---- end to end through the C-ABI with pinned host buffers
     h_goal = torch.from_numpy(goal_np).pin_memory()
@@ -281,18 +293,38 @@ def run_ours(args):
                  cost=torch.empty(B, dtype=torch.float64).pin_memory().numpy(),
                  iterations=torch.empty(B, dtype=torch.int32).pin_memory().numpy())
     h2d = h_goal.numel() * 8 + h_seed.numel() * 8
-    d2h = sum(v.nbytes for v in h_out.values())
     e2e_steps = max(1, min(args.steps, 5))
-    solver.solve_batch(params, h_goal.numpy(), h_seed.numpy(), first, out=h_out)
+    if world == 1:
+        d2h = sum(v.nbytes for v in h_out.values())
+
+        def step_e2e():
+            solver.solve_batch(params, h_goal.numpy(), h_seed.numpy(), first, out=h_out)
+    else:
+        # host goal poses in, the gathered results of every rank out (pinned), the NCCL all-gather in between
+        h_gathered = torch.empty((world, B, n + 3), dtype=torch.float64).pin_memory()
+        d2h = h_gathered.numel() * 8
+
+        def step_e2e():
+            solver.solve_batch_sharded_ptr(comm, params, B, first, h_goal.data_ptr(), h_seed.data_ptr(), 0,
+                                           h_gathered.data_ptr(), capi.MEM_HOST)
+    step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        solver.solve_batch(params, h_goal.numpy(), h_seed.numpy(), first, out=h_out)
+        step_e2e()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * B * e2e_steps / e2e_s
-    assert int((h_out["error_code"] == 1).sum()) == solved, "e2e and device-resident runs disagree"
+    e2e_solved = int((h_out["error_code"] == 1).sum()) if world == 1 else int((h_gathered[rank, :, n + 1] == 1).sum())
+    assert e2e_solved == solved, "e2e and device-resident runs disagree"
+    if world > 1:
+        # every rank holds every shard: the solved count over the whole job must agree across ranks
+        tot = torch.tensor([float((h_gathered[:, :, n + 1] == 1).sum())], dtype=torch.float64, device=dev)
+        lo, hi = tot.clone(), tot.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert lo.item() == hi.item(), "ranks disagree on the gathered results"
 
     if rank == 0:
         n_evals_gd = 2 * n + 3
@@ -336,6 +368,8 @@ def run_ours(args):
             "solved_frac": solved / B, "mean_generations": prob_gens / args.steps / B,
         }
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     solver.close()
     if world > 1:
         dist.destroy_process_group()

@@ -31,7 +31,8 @@ enum {
     PIK_E_CUDA = -4,
     PIK_E_NO_DEVICE = -5,
     PIK_E_OUT_OF_MEMORY = -6,
-    PIK_E_UNSUPPORTED = -7
+    PIK_E_UNSUPPORTED = -7,
+    PIK_E_NCCL = -8 /* NCCL missing or a collective failed: pik_comm_last_error() */
 };
 
 /* moveit_msgs::msg::MoveItErrorCodes values written by pick_ik_plugin.cpp:212,215 */
@@ -162,6 +163,35 @@ int pik_eval_cost(pik_solver* solver, const pik_params* params, int64_t B, const
                   int32_t* is_solution, double* tip_pose, int32_t memory);
 
 int pik_solver_synchronize(pik_solver* solver);
+
+/*
+ * Multi-GPU: one process (or host thread) per GPU, the pose batch sharded in contiguous ranges
+ * (SURVEY.md 8e).  Problems are independent, so the only exchange is one NCCL all-gather of the packed
+ * per-problem results at the end, issued on the solver's stream right behind the last kernel.
+ *
+ * pik_comm wraps an ncclComm_t that the library creates itself (NCCL is loaded with dlopen at the
+ * first call: single-GPU users need no NCCL).  Rank 0 calls pik_comm_unique_id and hands the 128
+ * bytes to the other ranks by any means (MPI, torch.distributed, a file); every rank then calls
+ * pik_comm_create.
+ */
+typedef struct pik_comm pik_comm;
+#define PIK_COMM_ID_BYTES 128
+int pik_comm_unique_id(void* id_out /* PIK_COMM_ID_BYTES */);
+int pik_comm_create(const void* id, int32_t n_ranks, int32_t rank, int32_t device, pik_comm** out);
+void pik_comm_destroy(pik_comm* comm);
+/* text of the last NCCL / loader error of this process (empty string if none) */
+const char* pik_comm_last_error(void);
+/*
+ * pik_solve_batch on this rank's shard (B_local problems, the same on every rank; RNG streams keyed
+ * by first_problem_index + local index = the global problem index), then the all-gather:
+ *   gathered [n_ranks][B_local][n + 3] doubles on every rank: joints[n], cost, error_code,
+ *   iterations (integers are exact in binary64), rank-major = global problem order when rank r owns
+ *   [r * B_local, (r + 1) * B_local).
+ * memory applies to goal_pose / seed / gathered alike.
+ */
+int pik_solve_batch_sharded(pik_solver* solver, pik_comm* comm, const pik_params* params, int64_t B_local,
+                            int64_t first_problem_index, const double* goal_pose, const double* seed,
+                            int64_t seed_stride, double* gathered, int32_t memory);
 
 /* number of CUDA devices visible (0 if none) */
 int pik_device_count(void);

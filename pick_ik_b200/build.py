@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpik_b200.so")
-SOURCES = ["pik_kernels.cu", "pik_api.cu"]
-HEADERS = ["pik_device.cuh", "pik_kernels.cuh", "pik_types.h", "pik_host_robot.h", os.path.join("..", "..", "include", "pik.h")]
+SOURCES = ["pik_kernels.cu", "pik_api.cu", "pik_comm.cu"]
+HEADERS = ["pik_device.cuh", "pik_kernels.cuh", "pik_types.h", "pik_host_robot.h", "pik_internal.h", os.path.join("..", "..", "include", "pik.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "--fmad=false",
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [
         os.path.join(CSRC, f) for f in SOURCES
-    ]
+    ] + ["-ldl"]  # NCCL itself is dlopen'ed at the first multi-GPU call (pik_comm.cu)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -29,7 +29,9 @@ EXPORTS = [
     "pik_robot_is_valid_configuration", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
     "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
     "pik_device_count", "pik_host_alloc", "pik_host_free", "pik_measure_fp64_peak",
+    "pik_comm_unique_id", "pik_comm_create", "pik_comm_destroy", "pik_comm_last_error", "pik_solve_batch_sharded",
 ]
+COMM_ID_BYTES = 128
 
 
 class PikError(RuntimeError):
@@ -117,6 +119,13 @@ def lib() -> C.CDLL:
     L.pik_host_free.restype = None
     L.pik_host_free.argtypes = [vp]
     L.pik_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.pik_comm_unique_id.argtypes = [vp]
+    L.pik_comm_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.pik_comm_destroy.restype = None
+    L.pik_comm_destroy.argtypes = [vp]
+    L.pik_comm_last_error.restype = C.c_char_p
+    L.pik_solve_batch_sharded.argtypes = [vp, vp, C.POINTER(Params), C.c_int64, C.c_int64, dp, dp, C.c_int64, dp,
+                                          C.c_int32]
     _lib = L
     return L
 
@@ -245,6 +254,15 @@ class Solver:
                                    solution, error_code, cost or None, iterations or None, memory)
         self._check(rc, "pik_solve_batch")
 
+    def solve_batch_sharded_ptr(self, comm: "Comm", params: Params, B_local: int, first_problem_index: int,
+                                goal_pose: int, seed: int, seed_stride: int, gathered: int, memory: int = MEM_DEVICE):
+        """This rank's shard + the NCCL all-gather of the packed results: gathered [n_ranks][B_local][n + 3]."""
+        rc = lib().pik_solve_batch_sharded(self.handle, comm.handle, C.byref(params), B_local, first_problem_index,
+                                           goal_pose, seed, seed_stride, gathered, memory)
+        if rc != PIK_OK:
+            raise PikError(rc, "pik_solve_batch_sharded",
+                           lib().pik_solver_last_error(self.handle).decode() or lib().pik_comm_last_error().decode())
+
     def synchronize(self):
         self._check(lib().pik_solver_synchronize(self.handle), "pik_solver_synchronize")
 
@@ -262,6 +280,37 @@ class Solver:
         h, self.handle = getattr(self, "handle", None), None
         if h and _lib is not None:
             _lib.pik_solver_destroy(h)
+
+    def __del__(self):
+        self.close()
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0); hand the bytes to every rank."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib().pik_comm_unique_id(buf)
+    if rc != PIK_OK:
+        raise PikError(rc, "pik_comm_unique_id", lib().pik_comm_last_error().decode())
+    return buf.raw
+
+
+class Comm:
+    """pik_comm: the library's own NCCL communicator for the sharded solve (one rank per GPU)."""
+
+    def __init__(self, unique_id: bytes, n_ranks: int, rank: int, device: int):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique_id must be COMM_ID_BYTES long")
+        h = C.c_void_p()
+        rc = lib().pik_comm_create(C.create_string_buffer(unique_id, COMM_ID_BYTES), n_ranks, rank, device, C.byref(h))
+        if rc != PIK_OK:
+            raise PikError(rc, "pik_comm_create", lib().pik_comm_last_error().decode())
+        self.handle = h
+        self.n_ranks, self.rank = n_ranks, rank
+
+    def close(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.pik_comm_destroy(h)
 
     def __del__(self):
         self.close()

@@ -11,6 +11,7 @@
 
 #include "../../include/pik.h"
 #include "pik_host_robot.h"
+#include "pik_internal.h"
 #include "pik_kernels.cuh"
 
 using namespace pik;
@@ -40,7 +41,7 @@ struct pik_solver {
     int32_t* h_counters = nullptr;            // pinned [2]
     unsigned long long* h_stats = nullptr;    // pinned [4]
     // staging for PIK_MEM_HOST calls
-    DeviceArray d_goal, d_seed, d_q, d_solution, d_error, d_cost, d_iters, d_issol, d_tip;
+    DeviceArray d_goal, d_seed, d_q, d_solution, d_error, d_cost, d_iters, d_issol, d_tip, d_packed, d_gather;
     // solver state
     DeviceArray d_pop, d_order, d_hdr, d_meta, d_active, d_counters, d_stats;
     pik_stats stats{};
@@ -292,7 +293,7 @@ void pik_solver_destroy(pik_solver* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     DeviceArray* arrays[] = {&s->d_goal, &s->d_seed, &s->d_q, &s->d_solution, &s->d_error, &s->d_cost, &s->d_iters,
-                             &s->d_issol, &s->d_tip, &s->d_pop, &s->d_order, &s->d_hdr, &s->d_meta, &s->d_active,
+                             &s->d_issol, &s->d_tip, &s->d_packed, &s->d_gather, &s->d_pop, &s->d_order, &s->d_hdr, &s->d_meta, &s->d_active,
                              &s->d_counters, &s->d_stats};
     for (DeviceArray* a : arrays) release(*a);
     if (s->h_counters) cudaFreeHost(s->h_counters);
@@ -305,12 +306,20 @@ void pik_solver_destroy(pik_solver* s) {
     delete s;
 }
 
-int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
-                    const double* goal_pose, const double* seed, int64_t seed_stride, double* solution,
-                    int32_t* error_code, double* cost, int32_t* iterations, int32_t memory) {
+}  // extern "C"
+
+namespace {
+
+// The solve behind pik_solve_batch.  keep_on_device: the results stay in the solver's device buffers
+// (d_solution, d_error, d_cost, d_iters) for a follow-up on the same stream (the sharded all-gather) and the
+// output pointers are ignored.
+int solve_core(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
+               const double* goal_pose, const double* seed, int64_t seed_stride, double* solution,
+               int32_t* error_code, double* cost, int32_t* iterations, int32_t memory, bool keep_on_device) {
     if (!s) return PIK_E_INVALID_ARGUMENT;
     s->last_error.clear();
-    if (!params || B < 0 || !goal_pose || !seed || !solution || !error_code) return PIK_E_INVALID_ARGUMENT;
+    if (!params || B < 0 || !goal_pose || !seed) return PIK_E_INVALID_ARGUMENT;
+    if (!keep_on_device && (!solution || !error_code)) return PIK_E_INVALID_ARGUMENT;
     const int n = s->robot.dev.n;
     if (seed_stride != 0 && seed_stride != n) return PIK_E_INVALID_ARGUMENT;
     if (memory != PIK_MEM_HOST && memory != PIK_MEM_DEVICE) return PIK_E_INVALID_ARGUMENT;
@@ -332,19 +341,22 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
     sb.first_problem_index = first_problem_index;
     sb.seed_stride = seed_stride;
     if (memory == PIK_MEM_HOST) {
-        if ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8)) ||
-            (rc = ensure(s, s->d_solution, (size_t)B * n * 8)) || (rc = ensure(s, s->d_error, (size_t)B * 4)) ||
-            (rc = ensure(s, s->d_cost, (size_t)B * 8)) || (rc = ensure(s, s->d_iters, (size_t)B * 4)))
-            return rc;
+        if ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8))) return rc;
         sb.goal_pose = static_cast<double*>(s->d_goal.ptr);
         sb.seed = static_cast<double*>(s->d_seed.ptr);
+    } else {
+        sb.goal_pose = goal_pose;
+        sb.seed = seed;
+    }
+    if (memory == PIK_MEM_HOST || keep_on_device) {
+        if ((rc = ensure(s, s->d_solution, (size_t)B * n * 8)) || (rc = ensure(s, s->d_error, (size_t)B * 4)) ||
+            (rc = ensure(s, s->d_cost, (size_t)B * 8)) || (rc = ensure(s, s->d_iters, (size_t)B * 4)))
+            return rc;
         sb.solution = static_cast<double*>(s->d_solution.ptr);
         sb.error_code = static_cast<int32_t*>(s->d_error.ptr);
         sb.cost = static_cast<double*>(s->d_cost.ptr);
         sb.iterations = static_cast<int32_t*>(s->d_iters.ptr);
     } else {
-        sb.goal_pose = goal_pose;
-        sb.seed = seed;
         sb.solution = solution;
         sb.error_code = error_code;
         sb.cost = cost;
@@ -413,7 +425,7 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
             list ^= 1;
         }
     }
-    if (memory == PIK_MEM_HOST) {
+    if (memory == PIK_MEM_HOST && !keep_on_device) {
         PIK_CUDA(s, cudaMemcpyAsync(solution, sb.solution, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));
         PIK_CUDA(s, cudaMemcpyAsync(error_code, sb.error_code, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
         if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, sb.cost, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
@@ -429,6 +441,17 @@ int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t 
     s->stats.gd_steps = (int64_t)s->h_stats[1];
     s->stats.solved = (int64_t)s->h_stats[2];
     return PIK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
+                    const double* goal_pose, const double* seed, int64_t seed_stride, double* solution,
+                    int32_t* error_code, double* cost, int32_t* iterations, int32_t memory) {
+    return solve_core(s, params, B, first_problem_index, goal_pose, seed, seed_stride, solution, error_code, cost,
+                      iterations, memory, false);
 }
 
 int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const double* goal_pose, const double* seed,
@@ -524,3 +547,28 @@ int pik_measure_fp64_peak(pik_solver* s, double* tflops) {
 }
 
 }  // extern "C"
+
+// ---- hooks for pik_comm.cu (pik_internal.h)
+int pik_internal_solver_device(const pik_solver* s) { return s ? s->device : -1; }
+int pik_internal_solver_num_variables(const pik_solver* s) { return s ? s->robot.dev.n : 0; }
+void* pik_internal_solver_stream(const pik_solver* s) { return s ? static_cast<void*>(s->stream) : nullptr; }
+
+int pik_internal_solve_keep(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
+                            const double* goal_pose, const double* seed, int64_t seed_stride, int32_t memory) {
+    return solve_core(s, params, B, first_problem_index, goal_pose, seed, seed_stride, nullptr, nullptr, nullptr, nullptr,
+                      memory, true);
+}
+
+int pik_internal_pack(pik_solver* s, int64_t B, size_t packed_elems, size_t gather_elems, double** packed, double** gather) {
+    if (!s || !packed || !gather) return PIK_E_INVALID_ARGUMENT;
+    int rc;
+    if ((rc = ensure(s, s->d_packed, packed_elems * sizeof(double)))) return rc;
+    if (gather_elems && (rc = ensure(s, s->d_gather, gather_elems * sizeof(double)))) return rc;
+    *packed = static_cast<double*>(s->d_packed.ptr);
+    *gather = gather_elems ? static_cast<double*>(s->d_gather.ptr) : nullptr;
+    PIK_CUDA(s, launch_pack_results(s->stream, B, s->robot.dev.n, static_cast<double*>(s->d_solution.ptr),
+                                    static_cast<double*>(s->d_cost.ptr), static_cast<int32_t*>(s->d_error.ptr),
+                                    static_cast<int32_t*>(s->d_iters.ptr), *packed));
+    s->stats.kernel_launches += 1;
+    return PIK_OK;
+}

@@ -849,6 +849,23 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 4 : 2) memeti
   }
 }
 
+// packed[b] = joints[n], cost, error_code, iterations: the row each rank contributes to the all-gather
+__global__ void pack_results_kernel(int64_t B, int n, const double* __restrict__ solution, const double* __restrict__ cost,
+                                    const int32_t* __restrict__ error_code, const int32_t* __restrict__ iterations,
+                                    double* __restrict__ packed) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = n + 3;
+    if (idx >= B * w) return;
+    const int64_t b = idx / w;
+    const int k = (int)(idx - b * w);
+    double v;
+    if (k < n) v = solution[b * n + k];
+    else if (k == n) v = cost[b];
+    else if (k == n + 1) v = (double)error_code[b];
+    else v = (double)iterations[b];
+    packed[idx] = v;
+}
+
 __global__ void fp64_peak_kernel(double* sink, int iters) {
     double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3,
            a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
@@ -974,6 +991,14 @@ cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int 
     const unsigned blocks = (unsigned)((n_active + per_block - 1) / per_block);
     PIK_DISPATCH_SPEC(spec, s.lanes_per_elite > 1, (memetic_generation_kernel<S><<<blocks, s.threads, s.smem, stream>>>(
                                 sb, list_in, s.lanes_per_elite, s.problems_per_warp, max_gens)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_results(cudaStream_t stream, int64_t B, int n, const double* solution, const double* cost,
+                                const int32_t* error_code, const int32_t* iterations, double* packed) {
+    if (B <= 0) return cudaSuccess;
+    const int64_t total = B * (n + 3);
+    pack_results_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(B, n, solution, cost, error_code, iterations, packed);
     return cudaGetLastError();
 }
 

@@ -40,6 +40,9 @@ cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int
 // bounds the grid.
 cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb,
                                       int list_in, int64_t n_active, int lanes_per_elite, int max_gens);
+// packed [B][n + 3] = joints, cost, error_code, iterations (the all-gather payload of the sharded solve)
+cudaError_t launch_pack_results(cudaStream_t stream, int64_t B, int n, const double* solution, const double* cost,
+                                const int32_t* error_code, const int32_t* iterations, double* packed);
 // FP64 FMA throughput microbenchmark (roofline denominator for the FP64 bound)
 cudaError_t launch_fp64_peak(cudaStream_t stream, double* sink, int blocks, int threads, int iters);
 cudaError_t configure_kernels();
