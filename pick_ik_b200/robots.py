@@ -211,4 +211,26 @@ def skew6() -> RobotChain:
     return RobotChain("skew6", "root", "tool", joints)
 
 
-ROBOTS = {"panda": panda, "ur5": ur5, "fetch": fetch, "rr": rr, "skew6": skew6}
+def snake16() -> RobotChain:
+    """Synthetic 16-variable chain at the variable-table limit (kMaxVars = 16): axis-aligned and general
+    revolute axes, two prismatic joints, two continuous joints, interleaved fixed joints and no tool frame
+    (no reference counterpart; maximum-size coverage for the device tables and loops)."""
+    R, F, P = JOINT_REVOLUTE, JOINT_FIXED, JOINT_PRISMATIC
+    axes = [(0, 0, 1), (0, 1, 0), (1, 0, 0), (0, 0, -1), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 0),
+            (0, -1, 0), (0, 0, 1), (0.2, 0.3, 0.9), (0, 1, 0), (1, 0, 0), (0, 0, 1), (0, 1, 0), (-1, 0, 0)]
+    joints = [Joint("base", F, (0.0, 0.0, 0.1), (0.0, 0.0, 0.2))]
+    for k, ax in enumerate(axes):
+        xyz = (0.09 if k % 3 == 0 else 0.02, 0.03 if k % 4 == 1 else 0.0, 0.07 if k % 2 else 0.11)
+        rpy = (0.3 * ((k % 5) - 2), 0.25 * ((k % 3) - 1), 0.4 * ((k % 7) - 3))
+        if k in (4, 11):
+            joints.append(Joint(f"s{k}", P, xyz, rpy, ax, -0.08, 0.12, 0.4))
+        elif k in (6, 13):
+            joints.append(Joint(f"s{k}", R, xyz, rpy, ax, velocity=2.0, continuous=True))
+        else:
+            joints.append(Joint(f"s{k}", R, xyz, rpy, ax, -2.2 + 0.05 * k, 2.4 - 0.04 * k, 1.0 + 0.1 * k))
+        if k == 7:
+            joints.append(Joint("mid", F, (0.01, 0.0, 0.02), (0.1, 0.0, -0.1)))
+    return RobotChain("snake16", "root", "s15_link", joints)
+
+
+ROBOTS = {"panda": panda, "ur5": ur5, "fetch": fetch, "rr": rr, "skew6": skew6, "snake16": snake16}

@@ -28,6 +28,11 @@ CASES = {
                                           memetic_max_generations=30), 64, "random"),
     "ur5_local": ("ur5", dict(mode="local"), 256, "perturbed"),
     "rr_local": ("rr", dict(mode="local", rotation_scale=1.0, position_threshold=1e-4), 64, "perturbed"),
+    # 16 variables (the table limit), prismatic + continuous + general-axis joints, minimal-displacement goal
+    "snake16_memetic": ("snake16", dict(mode="global", memetic_population_size=48, memetic_elite_size=5,
+                                        memetic_max_generations=12, memetic_gd_max_iters=10, position_threshold=0.02,
+                                        orientation_threshold=0.05, minimal_displacement_weight=0.01,
+                                        cost_threshold=0.2), 48, "random"),
 }
 
 
@@ -49,7 +54,10 @@ def inputs(name):
 
 
 def main():
+    only = set(sys.argv[1:])
     for name in CASES:
+        if only and name not in only:
+            continue
         chain, orobot, kw, goal, seed = inputs(name)
         res = orc.solve_batch(orobot, orc.default_params(**kw), goal, seed, first_problem_index=0)
         cost, is_sol, tip = orc.eval_cost_batch(orobot, orc.default_params(**kw), goal,

@@ -46,7 +46,7 @@ def check_solve(got, ref, label):
     np.testing.assert_array_equal(got["cost"], ref["cost"], err_msg=f"{label}: cost bit-equal")
 
 
-@pytest.mark.parametrize("name", ["rr", "panda", "ur5", "fetch", "skew6"])
+@pytest.mark.parametrize("name", ["rr", "panda", "ur5", "fetch", "skew6", "snake16"])
 @pytest.mark.parametrize("goals", [False, True])
 def test_eval_cost_bit_exact(solvers, name, goals):
     chain, orobot, solver = solvers(name)
@@ -70,7 +70,7 @@ def test_eval_cost_bit_exact(solvers, name, goals):
         assert 0 < s_ref.sum() < B
 
 
-@pytest.mark.parametrize("name", ["rr", "panda", "ur5", "fetch", "skew6"])
+@pytest.mark.parametrize("name", ["rr", "panda", "ur5", "fetch", "skew6", "snake16"])
 def test_gd_local_parity(solvers, name):
     chain, orobot, solver = solvers(name)
     op, gp = both_params(mode="local")
@@ -114,6 +114,13 @@ MEMETIC_CASES = [
     ("panda", dict(memetic_population_size=20, memetic_elite_size=1, memetic_max_generations=10), 100),
     ("fetch", dict(memetic_population_size=32, stop_optimization_on_valid_solution=0, memetic_max_generations=6), 100),
     ("panda", dict(memetic_population_size=16, return_approximate_solution=1, memetic_max_generations=3), 100),
+    # table limits: 16 variables (kMaxVars), 32 elites (kMaxElites), population 1024 (kMaxPopulation)
+    ("snake16", dict(memetic_population_size=40, memetic_elite_size=6, memetic_max_generations=8,
+                     memetic_gd_max_iters=6, position_threshold=0.02, orientation_threshold=0.05), 40),
+    ("panda", dict(memetic_population_size=64, memetic_elite_size=32, memetic_max_generations=4,
+                   memetic_gd_max_iters=5), 24),
+    ("rr", dict(memetic_population_size=1024, memetic_elite_size=3, memetic_max_generations=3,
+                memetic_gd_max_iters=4), 12),
 ]
 
 
