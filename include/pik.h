@@ -126,6 +126,21 @@ int pik_robot_get_variable(const pik_robot* robot, int32_t i, pik_variable* out)
 /* Robot::is_valid_configuration, src/robot.cpp:97-105 (host) */
 int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q);
 
+/*
+ * URDF -> chain table (host only; replaces the MoveIt RobotModel the reference reads in Robot::from,
+ * src/robot.cpp:44-85, and get_active_variable_indices, src/robot.cpp:122-160): the serial chain
+ * base_link -> tip_link of a URDF document as pik_joint_desc[] in root-to-tip order.  urdfdom / MoveIt
+ * semantics: rpy -> normalised quaternion -> rotation, default axis (1,0,0) normalised, <limit> intersected
+ * with <safety_controller> soft limits, continuous joints unbounded with the nominal range -pi..pi.
+ * *n_joints receives the chain length (also when capacity == 0 and out == NULL: size query).
+ * joint_names (optional): capacity * PIK_URDF_NAME_BYTES chars, one NUL-terminated name per joint.
+ * PIK_E_INVALID_ROBOT: malformed XML / tip not below base; PIK_E_UNSUPPORTED: floating, planar or mimic
+ * joints on the chain.
+ */
+#define PIK_URDF_NAME_BYTES 64
+int pik_urdf_chain(const char* urdf_xml, const char* base_link, const char* tip_link, pik_joint_desc* out,
+                   int32_t capacity, int32_t* n_joints, char* joint_names);
+
 /* stream: a cudaStream_t (or NULL for a stream owned by the solver) */
 int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_solver** out);
 void pik_solver_destroy(pik_solver* solver);

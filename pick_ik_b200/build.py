@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpik_b200.so")
-SOURCES = ["pik_kernels.cu", "pik_api.cu", "pik_comm.cu"]
+SOURCES = ["pik_kernels.cu", "pik_api.cu", "pik_comm.cu", "pik_urdf.cpp"]
 HEADERS = ["pik_device.cuh", "pik_kernels.cuh", "pik_types.h", "pik_host_robot.h", "pik_internal.h", os.path.join("..", "..", "include", "pik.h")]
 
 NVCC_FLAGS = [

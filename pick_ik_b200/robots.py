@@ -118,6 +118,36 @@ class RobotChain:
         return out
 
 
+def to_urdf(chain: RobotChain) -> str:
+    """The chain as a URDF document (links named after their parent joints; the decimal literals are
+    repr() round-trips, so pik_urdf_chain reproduces joint_desc() bit for bit).  Test fixture generator
+    for the C-ABI URDF reader -- the reference's robots live in URDFs this container does not have."""
+    def f(v):
+        return " ".join(repr(float(x)) for x in v)
+
+    lines = ['<?xml version="1.0"?>', f'<robot name="{chain.name}">', f'  <link name="{chain.base_link}"/>']
+    parent = chain.base_link
+    for k, j in enumerate(chain.joints):
+        child = chain.tip_link if k == len(chain.joints) - 1 else f"{j.name}_link"
+        kind = {JOINT_FIXED: "fixed", JOINT_PRISMATIC: "prismatic"}.get(j.type, "continuous" if j.continuous else "revolute")
+        lines.append(f'  <link name="{child}"/>')
+        lines.append(f'  <joint name="{j.name}" type="{kind}">')
+        lines.append(f'    <parent link="{parent}"/>')
+        lines.append(f'    <child link="{child}"/>')
+        lines.append(f'    <origin xyz="{f(j.xyz)}" rpy="{f(j.rpy)}"/>')
+        if j.type != JOINT_FIXED:
+            lines.append(f'    <axis xyz="{f(j.axis)}"/>')
+            if j.continuous:
+                lines.append(f'    <limit effort="10" velocity="{float(j.velocity)!r}"/>')
+            else:
+                lines.append(f'    <limit effort="10" lower="{float(j.lower)!r}" upper="{float(j.upper)!r}" '
+                             f'velocity="{float(j.velocity)!r}"/>')
+        lines.append("  </joint>")
+        parent = child
+    lines.append("</robot>")
+    return "\n".join(lines) + "\n"
+
+
 H = 1.57079632679  # the literal the URDFs carry
 
 
