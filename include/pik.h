@@ -133,13 +133,14 @@ int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q);
  * semantics: rpy -> normalised quaternion -> rotation, default axis (1,0,0) normalised, <limit> intersected
  * with <safety_controller> soft limits, continuous joints unbounded with the nominal range -pi..pi.
  * *n_joints receives the chain length (also when capacity == 0 and out == NULL: size query).
- * joint_names (optional): capacity * PIK_URDF_NAME_BYTES chars, one NUL-terminated name per joint.
+ * joint_names, link_names (optional): capacity * PIK_URDF_NAME_BYTES chars each, one NUL-terminated name per
+ * joint / per child link of that joint (the last link is the tip).
  * PIK_E_INVALID_ROBOT: malformed XML / tip not below base; PIK_E_UNSUPPORTED: floating, planar or mimic
  * joints on the chain.
  */
 #define PIK_URDF_NAME_BYTES 64
 int pik_urdf_chain(const char* urdf_xml, const char* base_link, const char* tip_link, pik_joint_desc* out,
-                   int32_t capacity, int32_t* n_joints, char* joint_names);
+                   int32_t capacity, int32_t* n_joints, char* joint_names, char* link_names);
 
 /* stream: a cudaStream_t (or NULL for a stream owned by the solver) */
 int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_solver** out);

@@ -120,7 +120,7 @@ def lib() -> C.CDLL:
     L.pik_host_free.restype = None
     L.pik_host_free.argtypes = [vp]
     L.pik_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
-    L.pik_urdf_chain.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp, C.c_int32, C.POINTER(C.c_int32), vp]
+    L.pik_urdf_chain.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp, C.c_int32, C.POINTER(C.c_int32), vp, vp]
     L.pik_comm_unique_id.argtypes = [vp]
     L.pik_comm_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.pik_comm_destroy.restype = None
@@ -291,12 +291,12 @@ def urdf_chain(urdf_xml: str, base_link: str, tip_link: str):
     """pik_urdf_chain: (joint_desc array in root-to-tip order, joint names) of the chain base_link -> tip_link."""
     n = C.c_int32()
     xml, base, tip = urdf_xml.encode(), base_link.encode(), tip_link.encode()
-    rc = lib().pik_urdf_chain(xml, base, tip, None, 0, C.byref(n), None)
+    rc = lib().pik_urdf_chain(xml, base, tip, None, 0, C.byref(n), None, None)
     if rc != PIK_OK:
         raise PikError(rc, "pik_urdf_chain")
     desc = np.zeros(n.value, dtype=JOINT_DESC_DTYPE)
     names = C.create_string_buffer(max(1, n.value) * URDF_NAME_BYTES)
-    rc = lib().pik_urdf_chain(xml, base, tip, desc.ctypes.data_as(C.c_void_p), n.value, C.byref(n), names)
+    rc = lib().pik_urdf_chain(xml, base, tip, desc.ctypes.data_as(C.c_void_p), n.value, C.byref(n), names, None)
     if rc != PIK_OK:
         raise PikError(rc, "pik_urdf_chain")
     raw = names.raw

@@ -160,7 +160,7 @@ void rpy_to_matrix(const double* rpy, double* R) {
 }  // namespace
 
 extern "C" int pik_urdf_chain(const char* urdf_xml, const char* base_link, const char* tip_link, pik_joint_desc* out,
-                              int32_t capacity, int32_t* n_joints, char* joint_names) {
+                              int32_t capacity, int32_t* n_joints, char* joint_names, char* link_names) {
     if (n_joints) *n_joints = 0;
     if (!urdf_xml || !base_link || !tip_link || !n_joints || capacity < 0 || (capacity > 0 && !out))
         return PIK_E_INVALID_ARGUMENT;
@@ -282,6 +282,11 @@ extern "C" int pik_urdf_chain(const char* urdf_xml, const char* base_link, const
             char* dst = joint_names + k * PIK_URDF_NAME_BYTES;
             std::memset(dst, 0, PIK_URDF_NAME_BYTES);
             std::strncpy(dst, j.name.c_str(), PIK_URDF_NAME_BYTES - 1);
+        }
+        if (link_names) {
+            char* dst = link_names + k * PIK_URDF_NAME_BYTES;
+            std::memset(dst, 0, PIK_URDF_NAME_BYTES);
+            std::strncpy(dst, j.child.c_str(), PIK_URDF_NAME_BYTES - 1);
         }
     }
     return PIK_OK;

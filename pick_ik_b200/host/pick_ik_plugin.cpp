@@ -196,6 +196,25 @@ void matrix_to_quat(double const* R, double* q) {  // Eigen Quaterniond(Matrix3d
 PickIKPlugin::PickIKPlugin() : impl_(new Impl) {}
 PickIKPlugin::~PickIKPlugin() = default;
 
+compat::ChainModel compat::chain_from_urdf(std::string const& urdf_xml, std::string const& group_name,
+                                           std::string const& base_link, std::string const& tip_link) {
+    int32_t n = 0;
+    int rc = pik_urdf_chain(urdf_xml.c_str(), base_link.c_str(), tip_link.c_str(), nullptr, 0, &n, nullptr, nullptr);
+    if (rc != PIK_OK) throw std::invalid_argument(std::string("chain_from_urdf: ") + pik_status_string(rc));
+    ChainModel m;
+    m.group_name = group_name;
+    m.model_frame = base_link;
+    m.joints.resize((size_t)n);
+    std::vector<char> jn((size_t)n * PIK_URDF_NAME_BYTES + 1), ln((size_t)n * PIK_URDF_NAME_BYTES + 1);
+    rc = pik_urdf_chain(urdf_xml.c_str(), base_link.c_str(), tip_link.c_str(), m.joints.data(), n, &n, jn.data(), ln.data());
+    if (rc != PIK_OK) throw std::invalid_argument(std::string("chain_from_urdf: ") + pik_status_string(rc));
+    for (int32_t k = 0; k < n; ++k) {
+        m.joint_names.emplace_back(jn.data() + (size_t)k * PIK_URDF_NAME_BYTES);
+        m.link_names.emplace_back(ln.data() + (size_t)k * PIK_URDF_NAME_BYTES);
+    }
+    return m;
+}
+
 bool PickIKPlugin::initialize(compat::ChainModel const& model, std::string const& group_name,
                               std::string const& base_frame, std::vector<std::string> const& tip_frames,
                               double /*search_discretization*/, int device) {

@@ -61,6 +61,12 @@ struct ChainModel {
     std::vector<std::string> link_names;   // child link of each joint; the last one is the tip link
 };
 
+// Stand-alone replacement for the RobotModel: the chain base_link -> tip_link of a URDF document
+// (pik_urdf_chain; urdfdom / MoveIt semantics).  Throws std::invalid_argument when the document is malformed,
+// the tip is not below the base, or the chain has a joint the engine does not support (floating, planar, mimic).
+ChainModel chain_from_urdf(std::string const& urdf_xml, std::string const& group_name, std::string const& base_link,
+                           std::string const& tip_link);
+
 }  // namespace compat
 
 // pick_ik::Params (generated from src/pick_ik_parameters.yaml by generate_parameter_library): same member

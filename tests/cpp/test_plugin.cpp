@@ -142,6 +142,38 @@ static void test_initialize_errors(bool have_gpu) {
     CHECK(!plugin.getPositionFK({}, {}, out));  // src/pick_ik_plugin.cpp:300-305
 }
 
+// the stand-alone path: URDF text -> ChainModel (pik_urdf_chain) -> the same table the hand-built model gives
+static void test_chain_from_urdf() {
+    char const* urdf =
+        "<?xml version='1.0'?><robot name='rr'><link name='base'/><link name='l1'/><link name='l2'/><link name='ee'/>"
+        "<!-- two revolute joints about z and a fixed tool frame -->"
+        "<joint name='j1' type='revolute'><parent link='base'/><child link='l1'/><axis xyz='0 0 1'/>"
+        "<limit lower='-3.0' upper='3.0' velocity='1' effort='1'/></joint>"
+        "<joint name='j2' type='revolute'><parent link='l1'/><child link='l2'/><origin xyz='2 0 0'/><axis xyz='0 0 1'/>"
+        "<limit lower='-3.0' upper='3.0' velocity='1' effort='1'/></joint>"
+        "<joint name='tool' type='fixed'><parent link='l2'/><child link='ee'/><origin xyz='1 0 0' rpy='0 0 0.25'/></joint>"
+        "</robot>";
+    auto const m = pick_ik_b200::compat::chain_from_urdf(urdf, "group", "base", "ee");
+    CHECK(m.joints.size() == 3 && m.joint_names.size() == 3 && m.link_names.size() == 3);
+    CHECK(m.joint_names[0] == "j1" && m.joint_names[2] == "tool" && m.link_names[2] == "ee" && m.model_frame == "base");
+    CHECK(m.joints[0].type == PIK_JOINT_REVOLUTE && m.joints[2].type == PIK_JOINT_FIXED);
+    CHECK(m.joints[1].origin_t[0] == 2.0 && m.joints[1].min_position == -3.0 && m.joints[1].max_velocity == 1.0);
+    double R[9];
+    rpy_to_matrix(0, 0, 0.25, R);
+    for (int i = 0; i < 9; ++i) CHECK(m.joints[2].origin_R[i] == R[i]);
+    pik_robot* robot = nullptr;
+    CHECK(pik_robot_create(m.joints.data(), (int32_t)m.joints.size(), &robot) == PIK_OK);
+    CHECK(pik_robot_num_variables(robot) == 2);
+    pik_robot_destroy(robot);
+    bool threw = false;
+    try {
+        pick_ik_b200::compat::chain_from_urdf(urdf, "group", "ee", "base");  // tip not below base
+    } catch (std::invalid_argument const&) {
+        threw = true;
+    }
+    CHECK(threw);
+}
+
 // tests/ik_tests.cpp:137-238 through the plugin, local mode, IkTestParams (:78-86)
 static void test_rr_ik() {
     PickIKPlugin plugin;
@@ -259,6 +291,7 @@ int main(int argc, char** argv) {
     bool const have_gpu = pik_device_count() > 0;
     test_params(yaml);
     test_initialize_errors(have_gpu);
+    test_chain_from_urdf();
     if (!cpu_only) {
         if (!have_gpu) {
             std::printf("no CUDA device: the solve sections need one\n");
