@@ -26,6 +26,26 @@ inline void host_mat_vec_add(const double* A, const double* v, const double* t, 
         out[r] = std::fma(A[3 * r + 2], v[2], std::fma(A[3 * r + 1], v[1], std::fma(A[3 * r], v[0], t[r])));
 }
 
+// does the constant rotation R have the sparsity pattern `cls` (exact tests: the device skips only entries that
+// ARE 0 or 1)?  An identity has every pattern.
+inline bool origin_has_pattern(const double* R, int cls) {
+    auto z = [&](int i) { return R[i] == 0.0; };
+    switch (cls) {
+        case kOrgGeneral: return true;
+        case kOrgRotX: return R[0] == 1.0 && z(1) && z(2) && z(3) && z(6);
+        case kOrgRotY: return R[4] == 1.0 && z(1) && z(3) && z(5) && z(7);
+        case kOrgRotZ: return R[8] == 1.0 && z(2) && z(5) && z(6) && z(7);
+        case kOrgIdentity: return origin_has_pattern(R, kOrgRotX) && origin_has_pattern(R, kOrgRotY) && origin_has_pattern(R, kOrgRotZ);
+        default: return false;
+    }
+}
+
+inline int classify_origin(const double* R) {
+    for (int cls : {kOrgIdentity, kOrgRotX, kOrgRotY, kOrgRotZ})
+        if (origin_has_pattern(R, cls)) return cls;
+    return kOrgGeneral;
+}
+
 // Fixed joints are folded into the constant origin of the next moving joint (or into the tip
 // transform); each moving joint becomes one chain step.
 inline int build_dev_robot(const pik_joint_desc* joints, int n_joints, DevRobot* out) {
@@ -84,7 +104,15 @@ inline int build_dev_robot(const pik_joint_desc* joints, int n_joints, DevRobot*
     if (have_acc) {
         std::memcpy(out->tip_R, accR, sizeof(accR));
         std::memcpy(out->tip_t, acct, sizeof(acct));
+    } else {
+        const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        std::memcpy(accR, I, sizeof(I));
+        acct[0] = acct[1] = acct[2] = 0.0;
     }
+    // the tip transform as entry n of the origin table (identity when the chain ends in a moving joint)
+    std::memcpy(out->R[n], accR, sizeof(accR));
+    std::memcpy(out->t[n], acct, sizeof(acct));
+    for (int i = 0; i <= n; ++i) out->ocls[i] = classify_origin(out->R[i]);
     // robot.cpp:69-82
     double divisor = 0.0;
     for (int i = 0; i < n; ++i) {

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "pik_device.cuh"
+#include "pik_host_robot.h"
 
 namespace pik {
 
@@ -905,19 +906,30 @@ size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 7) 
 // Compiled chain signatures (see StaticSpec).  kinds nibble: X 0, Y 1, Z 2, general 3, prismatic 4.
 // Every signature is compiled in two flavours: throughput (generation launches with one lane per elite,
 // gd_local, init) and wide (generation launches with several lanes per elite).
-constexpr unsigned long long kKindsAllZ7 = 0x2222222ull;  // Franka Panda and every 7-joint all-z (DH-style) arm + tool frame
-using SpecAllZ7T = StaticSpec<7, kKindsAllZ7, true, false>;
-using SpecAllZ7W = StaticSpec<7, kKindsAllZ7, true, true>;
-struct GenericSpecW : GenericSpec {
-    static constexpr bool kWide = true;
-};
+// Franka Panda and every 7-joint DH-style arm: all joints about z, every joint origin a rotation about x
+// (alpha_i = +-pi/2 or 0), tool frame a rotation about z
+constexpr unsigned long long kKindsAllZ7 = 0x2222222ull;
+using SpecAllZ7T = StaticSpec<7, kKindsAllZ7, true, false, kOrgRotX, kOrgRotZ>;
+using SpecAllZ7W = StaticSpec<7, kKindsAllZ7, true, true, kOrgRotX, kOrgRotZ>;
+using GenericSpecW = PatternSpec<kOrgGeneral, kOrgGeneral, true>;
+
+static bool origins_have_pattern(const DevRobot& rb, int origin_cls, int tip_cls) {
+    bool ok = origin_has_pattern(rb.R[rb.n], tip_cls);
+    for (int j = 1; j < rb.n; ++j) ok = ok && origin_has_pattern(rb.R[j], origin_cls);
+    return ok;
+}
 
 int select_spec(const DevRobot& rb) {
-    static const bool generic_only = std::getenv("PIK_GENERIC_ONLY") != nullptr;
-    if (generic_only) return kSpecGeneric;
+    // PIK_GENERIC_ONLY: the generic kernels; PIK_NO_STATIC: no compile-time n / kinds (pattern kernels only)
+    if (std::getenv("PIK_GENERIC_ONLY")) return kSpecGeneric;
     unsigned long long kinds = 0;
     for (int j = 0; j < rb.n; ++j) kinds |= (unsigned long long)(rb.kind[j] & 15) << (4 * j);
-    if (rb.n == 7 && kinds == kKindsAllZ7 && rb.has_tip) return kSpecAllZ7;
+    if (rb.n == 7 && kinds == kKindsAllZ7 && rb.has_tip && !std::getenv("PIK_NO_STATIC") &&
+        origins_have_pattern(rb, SpecAllZ7T::origin_cls, SpecAllZ7T::tip_cls))
+        return kSpecAllZ7;
+    if (origins_have_pattern(rb, kOrgIdentity, kOrgIdentity)) return kSpecOrgIdentity;
+    if (origins_have_pattern(rb, kOrgRotX, kOrgGeneral)) return kSpecOrgRotX;
+    if (origins_have_pattern(rb, kOrgRotY, kOrgGeneral)) return kSpecOrgRotY;
     return kSpecGeneric;
 }
 
@@ -926,6 +938,12 @@ int select_spec(const DevRobot& rb) {
     switch ((spec) * 2 + ((wide) ? 1 : 0)) {                                                           \
         case kSpecAllZ7 * 2: { using S = SpecAllZ7T; CALL; break; }                                    \
         case kSpecAllZ7 * 2 + 1: { using S = SpecAllZ7W; CALL; break; }                                \
+        case kSpecOrgIdentity * 2: { using S = PatternSpec<kOrgIdentity, kOrgIdentity, false>; CALL; break; } \
+        case kSpecOrgIdentity * 2 + 1: { using S = PatternSpec<kOrgIdentity, kOrgIdentity, true>; CALL; break; } \
+        case kSpecOrgRotX * 2: { using S = PatternSpec<kOrgRotX, kOrgGeneral, false>; CALL; break; }    \
+        case kSpecOrgRotX * 2 + 1: { using S = PatternSpec<kOrgRotX, kOrgGeneral, true>; CALL; break; } \
+        case kSpecOrgRotY * 2: { using S = PatternSpec<kOrgRotY, kOrgGeneral, false>; CALL; break; }    \
+        case kSpecOrgRotY * 2 + 1: { using S = PatternSpec<kOrgRotY, kOrgGeneral, true>; CALL; break; } \
         case kSpecGeneric * 2 + 1: { using S = GenericSpecW; CALL; break; }                            \
         default: { using S = GenericSpec; CALL; break; }                                               \
     }

@@ -28,9 +28,13 @@ cudaError_t upload_constants(cudaStream_t stream, const DevRobot& robot, const D
 cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double* goal_pose, const double* seed,
                              int64_t seed_stride, const double* q, double* cost, int32_t* is_solution,
                              double* tip_pose);
-// Chain signatures the kernels are compiled for (compile-time n, kind dispatch folded away); any other
-// robot runs the generic kernels.  select_spec() matches a robot table against them.
-enum : int { kSpecGeneric = 0, kSpecAllZ7 = 1, kSpecCount = 2 };
+// Chain signatures the kernels are compiled for; select_spec() picks the most specific one a robot table
+// matches.  kSpecAllZ7: n = 7, every joint about z, x-rotation origins, z-rotation tool frame (Franka Panda and
+// every DH-style 7R arm): n is a constant, the kind dispatch folds away.  kSpecOrg*: any n and kinds, but every
+// joint origin (from the second joint on) has the named sparsity pattern (OriginClass) -- identity (URDFs whose
+// origins only translate: Fetch), rotation about x, rotation about y (the UR family) -- so the chain walk
+// skips the terms that are exact zeros.  kSpecGeneric: anything.
+enum : int { kSpecGeneric = 0, kSpecAllZ7 = 1, kSpecOrgIdentity = 2, kSpecOrgRotX = 3, kSpecOrgRotY = 4, kSpecCount = 5 };
 int select_spec(const DevRobot& robot);
 
 cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb);

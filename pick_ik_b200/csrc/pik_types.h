@@ -11,6 +11,15 @@ constexpr int kMaxPopulation = 1024;
 
 enum StepKind : int { kRevX = 0, kRevY = 1, kRevZ = 2, kRevGeneral = 3, kPrismatic = 4 };
 
+// Sparsity pattern of a constant rotation (URDF origins are mostly rotations about one coordinate axis, often
+// by multiples of pi/2): entries that are exactly 0 or 1 need no arithmetic -- x * 1 == x and fma(x, 0, y) == y
+// exactly (up to the sign of an exact zero, which nothing on this path can observe) -- so a kernel compiled
+// for a chain signature whose origins all share a pattern skips them.  The skipped terms are the ones a full
+// product would add as exact zeros: results are bit-identical to the full left-to-right product of the
+// oracle.  (A run-time dispatch on the pattern was measured too: its branches cost what the skipped
+// arithmetic saves.)
+enum OriginClass : int { kOrgGeneral = 0, kOrgIdentity = 1, kOrgRotX = 2, kOrgRotY = 3, kOrgRotZ = 4 };
+
 // Flattened chain + variable table (constant memory on the device).  Fixed joints are folded into the
 // constant origin that precedes each moving joint, or into the tip transform.
 struct DevRobot {
@@ -21,8 +30,9 @@ struct DevRobot {
     int kind[kMaxVars];
     int bounded[kMaxVars];
     double sign[kMaxVars];
-    double R[kMaxVars][9];  // folded constant origin preceding each moving joint, row-major
-    double t[kMaxVars][3];
+    double R[kMaxVars + 1][9];  // folded constant origin preceding each moving joint, row-major; [n] = the tip transform
+    double t[kMaxVars + 1][3];
+    int ocls[kMaxVars + 1];     // OriginClass of R[j] (most specific pattern; used by select_spec)
     double axis[kMaxVars][3];
     double axis_sq[kMaxVars][6];  // xx yy zz xy xz yz
     double tip_R[9];

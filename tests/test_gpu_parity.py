@@ -148,6 +148,26 @@ def test_memetic_parity(solvers, name, kw, B, mapping, monkeypatch):
     assert st.kernel_launches >= 1
 
 
+@pytest.mark.parametrize("env", ["PIK_NO_STATIC", "PIK_GENERIC_ONLY"])
+@pytest.mark.parametrize("mode", ["global", "local"])
+def test_less_specific_chain_signatures(env, mode, monkeypatch):
+    """The Panda through the kernels of the less specific chain signatures it also matches: origin pattern
+    'rotation about x' with run-time n / kinds (PIK_NO_STATIC) and the fully generic kernels."""
+    monkeypatch.setenv(env, "1")
+    chain = robots.panda()
+    orobot = orc.build_robot(chain.joint_desc())
+    solver = capi.Solver(capi.Robot(chain))  # the signature is chosen when the solver is created
+    kw = dict(mode=mode, memetic_population_size=32, memetic_max_generations=40)
+    op, gp = both_params(**kw)
+    B = 160
+    goal = orc.make_targets(orobot, B)
+    seed = np.array(robots.PANDA_HOME) if mode == "global" else random_configs(orobot, B, 61)
+    for wide in ("0", "1000000000"):
+        monkeypatch.setenv("PIK_WIDE_WARPS_PER_SM", wide)
+        check_solve(solver.solve_batch(gp, goal, seed), orc.solve_batch(orobot, op, goal, seed), f"{env} {mode} {wide}")
+    solver.close()
+
+
 def test_memetic_seed_already_valid(solvers):
     chain, orobot, solver = solvers("panda")
     op, gp = both_params(mode="global")
