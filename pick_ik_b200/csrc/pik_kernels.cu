@@ -158,12 +158,12 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (5 * n + 7) * kS;
+    double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (5 * n + 12 + 7) * kS;
     const int64_t b = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (b >= sb.B) return;
     GdState st{base + lane, base + (size_t)n * kS + lane, base + (size_t)2 * n * kS + lane,
-               base + (size_t)3 * n * kS + lane, 0.0, 0.0};
-    double* g7 = base + (size_t)5 * n * kS + lane * 7;  // 7 contiguous doubles per lane
+               base + (size_t)3 * n * kS + lane, base + (size_t)5 * n * kS + lane, 0.0, 0.0};
+    double* g7 = base + (size_t)(5 * n + 12) * kS + lane * 7;  // 7 contiguous doubles per lane
     const double* sd = sb.seed + b * sb.seed_stride;
     for (int j = 0; j < n; ++j) {
         st.q[j * kS] = sd[j];
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
         st.local_cost = st.best_cost = c0;  // GradientIk::from
         double previous_cost = 0.0;
         while (iters < c_pr.gd_max_iters) {
-            const bool improved = gd_step<S>(st, g7, sd, aux);
+            const bool improved = gd_step<S, true>(st, g7, sd, aux);
             ++steps;
             // best == local when improved, so aux describes best (ik_gradient.cpp:117-121)
             if (improved && c_pr.stop_on_valid && solution_from_aux(aux)) {
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 4 : 2) memeti
         __syncwarp();
         double best_cost = 0.0;
         if (L == 1) {
-            GdState st{W.q + c, W.g + c, W.best + c, W.sc + c, 0.0, 0.0};
+            GdState st{W.q + c, W.g + c, W.best + c, W.sc + c, nullptr, 0.0, 0.0};
             const double* g7 = W.goal + 7 * (valid ? k : 0);
             if (valid) st.local_cost = st.best_cost = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, nullptr);
             bool going = valid;
@@ -895,13 +895,13 @@ MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
     s.problems_per_warp = 32 / (E * L);
     s.warps = L == 1 ? kWarpsPerBlockBulk : kWarpsPerBlock;
     // a large population may not leave room for 8 warps' worth of shared memory
-    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, s.problems_per_warp) > 110 * 1024) s.warps >>= 1;
+    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, s.problems_per_warp) > 112 * 1024) --s.warps;
     s.threads = 32 * s.warps;
     s.smem = s.warps * warp_smem_bytes(n, P, s.problems_per_warp);
     return s;
 }
 
-size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 7) * kS * sizeof(double); }
+size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 12 + 7) * kS * sizeof(double); }
 
 // Compiled chain signatures (see StaticSpec).  kinds nibble: X 0, Y 1, Z 2, general 3, prismatic 4.
 // Every signature is compiled in two flavours: throughput (generation launches with one lane per elite,
