@@ -906,11 +906,11 @@ size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 12 
 // Compiled chain signatures (see StaticSpec).  kinds nibble: X 0, Y 1, Z 2, general 3, prismatic 4.
 // Every signature is compiled in two flavours: throughput (generation launches with one lane per elite,
 // gd_local, init) and wide (generation launches with several lanes per elite).
-// Franka Panda and every 7-joint DH-style arm: all joints about z, every joint origin a rotation about x
+// Franka Panda and every 7-joint DH-style arm: all joints about +z, every joint origin a rotation about x
 // (alpha_i = +-pi/2 or 0), tool frame a rotation about z
 constexpr unsigned long long kKindsAllZ7 = 0x2222222ull;
-using SpecAllZ7T = StaticSpec<7, kKindsAllZ7, true, false, kOrgRotX, kOrgRotZ>;
-using SpecAllZ7W = StaticSpec<7, kKindsAllZ7, true, true, kOrgRotX, kOrgRotZ>;
+using SpecAllZ7T = StaticSpec<7, kKindsAllZ7, true, false, kOrgRotX, kOrgRotZ, true>;
+using SpecAllZ7W = StaticSpec<7, kKindsAllZ7, true, true, kOrgRotX, kOrgRotZ, true>;
 using GenericSpecW = PatternSpec<kOrgGeneral, kOrgGeneral, true>;
 
 static bool origins_have_pattern(const DevRobot& rb, int origin_cls, int tip_cls) {
@@ -924,7 +924,9 @@ int select_spec(const DevRobot& rb) {
     if (std::getenv("PIK_GENERIC_ONLY")) return kSpecGeneric;
     unsigned long long kinds = 0;
     for (int j = 0; j < rb.n; ++j) kinds |= (unsigned long long)(rb.kind[j] & 15) << (4 * j);
-    if (rb.n == 7 && kinds == kKindsAllZ7 && rb.has_tip && !std::getenv("PIK_NO_STATIC") &&
+    bool unit_sign = true;
+    for (int j = 0; j < rb.n; ++j) unit_sign = unit_sign && rb.sign[j] == 1.0;
+    if (rb.n == 7 && kinds == kKindsAllZ7 && rb.has_tip && unit_sign && !std::getenv("PIK_NO_STATIC") &&
         origins_have_pattern(rb, SpecAllZ7T::origin_cls, SpecAllZ7T::tip_cls))
         return kSpecAllZ7;
     if (origins_have_pattern(rb, kOrgIdentity, kOrgIdentity)) return kSpecOrgIdentity;
