@@ -1006,7 +1006,32 @@ cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int
 cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb,
                                       int list_in, int64_t n_active, int lanes_per_elite, int max_gens) {
     if (n_active <= 0) return cudaSuccess;
-    const MemeticShape s = memetic_shape(n, P, E, lanes_per_elite);
+    MemeticShape s = memetic_shape(n, P, E, lanes_per_elite);
+    {
+        // A throughput-mode launch that does not fill the machine is bound by its most loaded SM: pick the CTA size (in warps)
+        // that minimises the warps on that SM when the CTAs are dealt round-robin (ties: the larger CTA).
+        static const int sm_count = [] {
+            int dev = 0, v = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+            return v > 0 ? v : 148;
+        }();
+        const int64_t n_warps = (n_active + s.problems_per_warp - 1) / s.problems_per_warp;
+        if (s.lanes_per_elite == 1 && n_warps <= (int64_t)sm_count * 16 && !std::getenv("PIK_FIXED_CTA")) {
+            int best_w = s.warps;
+            int64_t best_load = INT64_MAX;
+            for (int w = s.warps; w >= 1; --w) {
+                const int64_t ctas = (n_warps + w - 1) / w;
+                const int64_t load = ((ctas + sm_count - 1) / sm_count) * w;
+                if (load < best_load) {
+                    best_load = load;
+                    best_w = w;
+                }
+            }
+            s.warps = best_w;
+            s.threads = 32 * s.warps;
+            s.smem = s.warps * warp_smem_bytes(n, P, s.problems_per_warp);
+        }
+    }
     const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
     const unsigned blocks = (unsigned)((n_active + per_block - 1) / per_block);
     PIK_DISPATCH_SPEC(spec, s.lanes_per_elite > 1, (memetic_generation_kernel<S><<<blocks, s.threads, s.smem, stream>>>(
