@@ -100,11 +100,11 @@ bool trace_each_generation() { return std::getenv("PIK_TRACE_GENERATIONS") != nu
 // whole GD instance per lane, 32 / E problems per warp) executes the fewest instructions per problem but has
 // the longest serial path per generation; as the batch drains, the warp's lanes are spread over the
 // evaluations of each GD step instead (L lanes per elite): the largest L that still keeps about
-// `warps_per_sm` warps per SM.  PIK_WIDE_WARPS_PER_SM overrides the target (read per call: the parity tests
+// `warps_per_sm` warps per SM (12 = 3 CTAs of the wide flavour, which runs at 168 registers without spills).  PIK_WIDE_WARPS_PER_SM overrides the target (read per call: the parity tests
 // run both mappings; 0 = always throughput mode, huge = always the widest mapping).
 int lanes_for(int64_t n_active, int E, int sm_count) {
     const char* env = std::getenv("PIK_WIDE_WARPS_PER_SM");
-    const int64_t warps_per_sm = env ? std::atoll(env) : (int64_t)16;
+    const int64_t warps_per_sm = env ? std::atoll(env) : (int64_t)12;  // what the wide flavour keeps resident
     const int64_t capacity_lanes = (int64_t)sm_count * warps_per_sm * 32;
     const int lmax = memetic_max_lanes_per_elite(E);
     int L = 1;

@@ -457,14 +457,15 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
 // One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for PW problems per warp.
 // -----------------------------------------------------------------------------------------------
 // Register budgets: the throughput flavour (and the generic kernel, which serves both modes) runs 2 CTAs of
-// 8 warps per SM at 128 registers; the wide flavour (several lanes per elite) small CTAs of 4 warps.
+// 8 warps per SM at 128 registers; the wide flavour (several lanes per elite) 3 CTAs of 4 warps at 168 registers
+// (no spills: a lone warp pays the full latency of every local-memory access).
 //
 // max_gens: generations this launch may run per problem.  Throughput launches run one (the host compacts the
 // active list between launches).  A launch with one problem per warp (PW == 1) may run many: the warp keeps
 // its problem until it is solved, has failed or has used its budget -- problems are independent, so the tail
 // of the batch needs no global step between generations and the hardware block scheduler balances the load.
 template <class S>
-__global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 4 : 2) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
+__global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
                                                                       int list_in, int L, int PW, int max_gens) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
