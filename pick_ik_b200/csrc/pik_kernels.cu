@@ -495,7 +495,11 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     __syncwarp();
 
   for (int gen_here = 0;; ++gen_here) {
+#ifdef PIK_PHASE_TRACE  // build with -DPIK_PHASE_TRACE: PIK_DEBUG_PHASES=1 prints per-phase cycle counts (costs a stack frame)
     const bool dbg = c_pr.debug && blockIdx.x == 0 && warp == 0 && lane == 0;
+#else
+    constexpr bool dbg = false;
+#endif
     long long t_start = 0, t_gd = 0, t_rep = 0, t_sort = 0, t_book = 0;
     if (dbg) t_start = clock64();
     // ---- gradientDescent(i) for every elite (src/ik_memetic.cpp:66-91, 230-239)
