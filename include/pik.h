@@ -123,6 +123,9 @@ int pik_robot_create(const pik_joint_desc* joints, int32_t n_joints, pik_robot**
 void pik_robot_destroy(pik_robot* robot);
 int32_t pik_robot_num_variables(const pik_robot* robot);
 int pik_robot_get_variable(const pik_robot* robot, int32_t i, pik_variable* out);
+/* name of the compiled chain signature the kernels will use for this robot (host; informational):
+ * "generic", "all-z 7R, x-rotation origins (static)", "identity origins", "x-rotation origins", "y-rotation origins" */
+const char* pik_robot_chain_signature(const pik_robot* robot);
 /* Robot::is_valid_configuration, src/robot.cpp:97-105 (host) */
 int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q);
 

@@ -26,7 +26,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 EXPORTS = [
     "pik_version", "pik_status_string", "pik_params_default", "pik_params_validate", "pik_robot_create",
     "pik_robot_destroy", "pik_robot_num_variables", "pik_robot_get_variable",
-    "pik_robot_is_valid_configuration", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
+    "pik_robot_is_valid_configuration", "pik_robot_chain_signature", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
     "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
     "pik_device_count", "pik_host_alloc", "pik_host_free", "pik_measure_fp64_peak",
     "pik_urdf_chain", "pik_comm_unique_id", "pik_comm_create", "pik_comm_destroy", "pik_comm_last_error", "pik_solve_batch_sharded",
@@ -105,6 +105,8 @@ def lib() -> C.CDLL:
     L.pik_robot_num_variables.argtypes = [vp]
     L.pik_robot_get_variable.argtypes = [vp, C.c_int32, C.POINTER(Variable)]
     L.pik_robot_is_valid_configuration.argtypes = [vp, dp]
+    L.pik_robot_chain_signature.restype = C.c_char_p
+    L.pik_robot_chain_signature.argtypes = [vp]
     L.pik_solver_create.argtypes = [vp, C.c_int32, vp, C.POINTER(vp)]
     L.pik_solver_destroy.restype = None
     L.pik_solver_destroy.argtypes = [vp]
@@ -178,6 +180,9 @@ class Robot:
         if rc != PIK_OK:
             raise PikError(rc, "pik_robot_get_variable")
         return v
+
+    def chain_signature(self) -> str:
+        return lib().pik_robot_chain_signature(self.handle).decode()
 
     def is_valid_configuration(self, q) -> bool:
         qa = np.ascontiguousarray(q, dtype=np.float64)

@@ -234,6 +234,17 @@ int pik_robot_get_variable(const pik_robot* robot, int32_t i, pik_variable* out)
     return PIK_OK;
 }
 
+const char* pik_robot_chain_signature(const pik_robot* robot) {
+    if (!robot) return "";
+    switch (select_spec(robot->dev)) {
+        case kSpecAllZ7: return "all-z 7R, x-rotation origins (static)";
+        case kSpecOrgIdentity: return "identity origins";
+        case kSpecOrgRotX: return "x-rotation origins";
+        case kSpecOrgRotY: return "y-rotation origins";
+        default: return "generic";
+    }
+}
+
 int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q) {
     if (!robot || !q) return 0;
     for (int i = 0; i < robot->dev.n; ++i) {

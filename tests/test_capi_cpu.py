@@ -101,3 +101,11 @@ def test_status_strings_and_no_device():
         with pytest.raises(capi.PikError) as e:
             capi.Solver(capi.Robot(robots.panda()))
         assert e.value.status == -5  # PIK_E_NO_DEVICE: the product path fails loudly without a GPU
+
+
+def test_chain_signatures():
+    """select_spec: the most specific compiled chain signature each fixture robot matches (host-side)."""
+    expect = {"panda": "all-z 7R, x-rotation origins (static)", "ur5": "y-rotation origins", "fetch": "identity origins",
+              "rr": "identity origins", "skew6": "generic", "snake16": "generic"}
+    for name, sig in expect.items():
+        assert capi.Robot(robots.ROBOTS[name]()).chain_signature() == sig, name
