@@ -263,4 +263,20 @@ def snake16() -> RobotChain:
     return RobotChain("snake16", "root", "s15_link", joints)
 
 
-ROBOTS = {"panda": panda, "ur5": ur5, "fetch": fetch, "rr": rr, "skew6": skew6, "snake16": snake16}
+def single(kind: str = "revolute") -> RobotChain:
+    """One moving joint (the smallest chain the engine accepts): a revolute joint about a general axis or a
+    prismatic joint, between two fixed joints (minimum-size coverage: n = 1, 1/n mutation probability = 1)."""
+    if kind == "revolute":
+        moving = Joint("j", JOINT_REVOLUTE, (0.1, 0.0, 0.2), (0.2, -0.1, 0.3), (0.0, 0.6, 0.8), -2.0, 2.5, 1.0)
+    else:
+        moving = Joint("j", JOINT_PRISMATIC, (0.1, 0.0, 0.2), (0.2, -0.1, 0.3), (0.0, 0.0, 1.0), -0.3, 0.4, 0.5)
+    return RobotChain("single_" + kind, "root", "tool",
+                      [Joint("pre", JOINT_FIXED, (0.0, 0.1, 0.0), (0.0, 0.3, 0.0)), moving,
+                       Joint("post", JOINT_FIXED, (0.3, 0.0, 0.1), (0.1, 0.0, 0.0))])
+
+
+def single_prismatic() -> RobotChain:
+    return single("prismatic")
+
+
+ROBOTS = {"single": single, "single_prismatic": single_prismatic, "panda": panda, "ur5": ur5, "fetch": fetch, "rr": rr, "skew6": skew6, "snake16": snake16}

@@ -70,7 +70,7 @@ def test_eval_cost_bit_exact(solvers, name, goals):
         assert 0 < s_ref.sum() < B
 
 
-@pytest.mark.parametrize("name", ["rr", "panda", "ur5", "fetch", "skew6", "snake16"])
+@pytest.mark.parametrize("name", ["single", "single_prismatic", "rr", "panda", "ur5", "fetch", "skew6", "snake16"])
 def test_gd_local_parity(solvers, name):
     chain, orobot, solver = solvers(name)
     op, gp = both_params(mode="local")
@@ -121,6 +121,10 @@ MEMETIC_CASES = [
                    memetic_gd_max_iters=5), 24),
     ("rr", dict(memetic_population_size=1024, memetic_elite_size=3, memetic_max_generations=3,
                 memetic_gd_max_iters=4), 12),
+    # one moving joint (n = 1): every gene mutates with probability 1
+    ("single", dict(memetic_population_size=12, memetic_elite_size=2, memetic_max_generations=6, rotation_scale=0.0), 40),
+    ("single_prismatic", dict(memetic_population_size=8, memetic_elite_size=1, memetic_max_generations=6,
+                              rotation_scale=0.0), 40),
 ]
 
 
