@@ -161,7 +161,7 @@ inline DevParams make_dev_params(const pik_params& p) {
         d.round_key[2 * r + 1] = d.seed_hi + 0xBB67AE85u * static_cast<uint32_t>(r);
     }
     d.debug = std::getenv("PIK_DEBUG_PHASES") ? 1 : 0;
-    d.lockstep = std::getenv("PIK_NO_LOCKSTEP") ? 0 : 1;
+    d.lockstep = std::getenv("PIK_NO_LOCKSTEP") ? 0 : (std::getenv("PIK_LOCKSTEP_MASK") ? std::atoi(std::getenv("PIK_LOCKSTEP_MASK")) : 3);
     return d;
 }
 

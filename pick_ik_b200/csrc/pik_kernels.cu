@@ -474,12 +474,13 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * PW;
     // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
     // GD step (below): warps that run the same code at the same time share their instruction-cache fills.
-    const bool lockstep = L == 1 && c_pr.lockstep != 0;
+    const bool lockstep = L == 1 && (c_pr.lockstep & 1) != 0;
+    const bool lockstep_rep = L == 1 && (c_pr.lockstep & 2) != 0;
     if (base >= n_active) {
-        if (lockstep) {
+        if (lockstep)
             for (int step = 0; step < c_pr.gd_max_iters; ++step) __syncthreads();
+        if (lockstep_rep)
             for (int k = 0; k < PW; ++k) __syncthreads();
-        }
         return;
     }
     const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, PW), n, P, PW);
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     const double inv_n = 1.0 / (double)n;
     int n_problems = 0;
     for (int k = 0; k < PW; ++k) {
-        if (lockstep) __syncthreads();  // re-align the CTA's warps at every problem (instruction-cache sharing)
+        if (lockstep_rep) __syncthreads();  // re-align the CTA's warps at every problem (instruction-cache sharing)
         const int b = W.pidx[k];
         if (b < 0) continue;
         ++n_problems;
