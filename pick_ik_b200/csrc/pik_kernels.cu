@@ -7,11 +7,13 @@
 //                              gradientDescent on the elites, reproduce, sortPopulation, solution test, checkWipeout
 //
 // Mapping.  The unit of work is one cost evaluation (FK chain walk + pose/goal costs): a serial FP64
-// dependency chain of ~10^3 operations.  Every WARP is autonomous -- it owns PW problems end to end and
-// never meets a block barrier:
-//   * elite local search: one GD instance per lane (L = 1), every lane carrying whole finite-difference
-//     + line-search steps of its own elite; or, when the batch has nearly drained and latency is all that
-//     is left, L lanes per elite with the 2n finite-difference evaluations of a step spread over them;
+// dependency chain of ~10^3 operations.  Every WARP is autonomous -- it owns PW problems end to end (the only
+// block barriers are the optional lockstep ones of the throughput mapping, which exchange no data):
+//   * elite local search: one GD instance per lane (L = 1, throughput mapping), every lane carrying whole
+//     finite-difference + line-search steps of its own elite as frame pairs (gd_step_compact); or, once the
+//     batch has drained so far that a launch is bound by the serial path of a generation, L lanes per elite
+//     (wide mapping, gd_elite_wide): the finite-difference pairs and the accepted point of the previous step
+//     in one round, the two line-search points in a second;
 //   * reproduction: the warp walks each problem's children in windows of 32 (one child per lane); the
 //     sequential mating-pool semantics of the reference are kept by committing a window only up to the
 //     first child that removes a parent and restarting after it with the shrunken pool;
