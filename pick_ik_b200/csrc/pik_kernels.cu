@@ -657,7 +657,9 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                     // empty pool: a random individual seeded from the slot's previous occupant
                     const Stream st = make_stream((uint32_t)(sb.first_problem_index + b), kStreamRandomChild,
                                                   (uint32_t)iter, (uint32_t)i);
-                    for (int j = 0; j < n; ++j) col[j * kS] = src[(size_t)j * P + slot];
+                    // (only an unbounded variable reads its previous value, robot.cpp:23-30; the child slots of a fresh
+                    // population are written for robots with such variables only)
+                    for (int j = 0; j < n; ++j) col[j * kS] = c_rb.bounded[j] ? 0.0 : src[(size_t)j * P + slot];
                     random_valid_configuration(st, col);
                     for (int j = 0; j < n; ++j) {
                         dst[(size_t)j * P + slot] = col[j * kS];
