@@ -32,7 +32,8 @@ enum {
     PIK_E_NO_DEVICE = -5,
     PIK_E_OUT_OF_MEMORY = -6,
     PIK_E_UNSUPPORTED = -7,
-    PIK_E_NCCL = -8 /* NCCL missing or a collective failed: pik_comm_last_error() */
+    PIK_E_NCCL = -8, /* NCCL missing or a collective failed: pik_comm_last_error() */
+    PIK_E_BUSY = -9  /* a pik_solve_batch_async is in flight on this solver: pik_solver_wait first */
 };
 
 /* moveit_msgs::msg::MoveItErrorCodes values written by pick_ik_plugin.cpp:212,215 */
@@ -85,8 +86,8 @@ typedef struct pik_params {
     double memetic_wipeout_fitness_tol;
     double memetic_gd_max_time; /* accepted, ignored: replaced by memetic_gd_max_iters */
     int32_t stop_optimization_on_valid_solution;
-    int32_t memetic_num_threads;            /* species; the batch API runs one (ik_memetic.cpp:299) */
-    int32_t memetic_stop_on_first_solution;
+    int32_t memetic_num_threads;            /* species per problem (ik_memetic.cpp:315-370), run in lockstep */
+    int32_t memetic_stop_on_first_solution; /* the first species to return a value terminates the others */
     int32_t memetic_population_size;
     int32_t memetic_elite_size;
     int32_t memetic_max_generations;
@@ -170,6 +171,22 @@ int pik_solve_batch(pik_solver* solver, const pik_params* params, int64_t B,
                     int64_t first_problem_index, const double* goal_pose, const double* seed,
                     int64_t seed_stride, double* solution, int32_t* error_code, double* cost,
                     int32_t* iterations, int32_t memory);
+
+/*
+ * The same solve without waiting for it: every copy and kernel of the call is enqueued on the solver's stream
+ * (the kernels size themselves from device-side counters, so the host reads nothing back while the solve runs)
+ * and the call returns.  The buffers must stay valid and the results may be read only after pik_solver_wait
+ * (host outputs should be page-locked, pik_host_alloc, for the copies to be asynchronous).  One solve in flight
+ * per solver: a second call returns PIK_E_BUSY; use one solver (own stream) per batch in flight -- solvers of
+ * the same robot and parameters run concurrently on one device, e.g. the head of batch k + 1 in the shadow of
+ * the latency-bound tail of batch k.  pik_solver_query: 1 = nothing in flight or finished, 0 = still running.
+ */
+int pik_solve_batch_async(pik_solver* solver, const pik_params* params, int64_t B,
+                          int64_t first_problem_index, const double* goal_pose, const double* seed,
+                          int64_t seed_stride, double* solution, int32_t* error_code, double* cost,
+                          int32_t* iterations, int32_t memory);
+int pik_solver_wait(pik_solver* solver);
+int pik_solver_query(pik_solver* solver);
 
 /*
  * Batched FK + cost + solution test: make_cost_fn (src/goal.cpp:188-203),

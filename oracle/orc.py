@@ -63,6 +63,7 @@ class Params(C.Structure):
                 ("stop_optimization_on_valid_solution", C.c_int32), ("memetic_population_size", C.c_int32),
                 ("memetic_elite_size", C.c_int32), ("memetic_max_generations", C.c_int32),
                 ("memetic_gd_max_iters", C.c_int32), ("return_approximate_solution", C.c_int32),
+                ("memetic_num_threads", C.c_int32), ("memetic_stop_on_first_solution", C.c_int32),
                 ("rng_seed", C.c_uint64)]
 
 

@@ -537,6 +537,8 @@ void orc_params_default(orc_params* p) {
     p->memetic_max_generations = 100;
     p->memetic_gd_max_iters = 25;
     p->return_approximate_solution = 0;
+    p->memetic_num_threads = 1;
+    p->memetic_stop_on_first_solution = 1;
     p->rng_seed = 0x5EED;
 }
 
@@ -751,6 +753,7 @@ typedef struct {
     orc_ctx cx;
     int n, P, E;
     uint32_t problem_index;
+    uint32_t species; /* replica index (MemeticIkParams::num_threads); high half of the individual word */
     orc_individual* pop;
     orc_individual* scratch;
     int* order;
@@ -781,7 +784,7 @@ static void init_population(orc_memetic* m, const double* initial_guess) {
         if (i > 0) {
             orc_stream st;
             stream_init(&st, m->cx.pb->params->rng_seed, m->problem_index, STREAM_INIT, m->init_epoch,
-                        (uint32_t)i);
+                        (uint32_t)i | (m->species << 16));
             set_random_valid_configuration(robot, &st, ind->genes);
         }
         ind->fitness = cost_counted(&m->cx, ind->genes);
@@ -838,7 +841,7 @@ static void reproduce(orc_memetic* m, uint32_t generation) {
         if (pool_size > 0) {
             orc_stream st;
             stream_init(&st, m->cx.pb->params->rng_seed, m->problem_index, STREAM_REPRODUCE, generation,
-                        (uint32_t)i);
+                        (uint32_t)i | (m->species << 16));
             uint32_t b0[4], b1[4];
             stream_block(&st, 0, b0);
             stream_block(&st, 1, b1);
@@ -895,7 +898,7 @@ static void reproduce(orc_memetic* m, uint32_t generation) {
         } else {
             orc_stream st;
             stream_init(&st, m->cx.pb->params->rng_seed, m->problem_index, STREAM_RANDOM_CHILD, generation,
-                        (uint32_t)i);
+                        (uint32_t)i | (m->species << 16));
             set_random_valid_configuration(robot, &st, child->genes);
             child->fitness = cost_counted(&m->cx, child->genes);
             for (int j = 0; j < n; ++j) child->gradient[j] = 0.0;
@@ -942,7 +945,57 @@ static int check_wipeout(orc_memetic* m) {
     return 0;
 }
 
-/* ik_memetic.cpp:285-296 + 211-283 */
+/* MemeticIk::from + the first initPopulation (ik_memetic.cpp:18-41, 221-223) */
+static void memetic_begin(orc_memetic* m, const orc_problem* pb, const double* initial_guess,
+                          uint32_t problem_index, uint32_t species) {
+    const orc_params* p = pb->params;
+    const int n = pb->robot->n;
+    memset(m, 0, sizeof(*m));
+    m->cx.pb = pb;
+    m->n = n;
+    m->P = p->memetic_population_size;
+    m->E = p->memetic_elite_size;
+    m->problem_index = problem_index;
+    m->species = species;
+    m->pop = (orc_individual*)calloc((size_t)m->P, sizeof(orc_individual));
+    m->scratch = (orc_individual*)calloc((size_t)m->P, sizeof(orc_individual));
+    m->order = (int*)calloc((size_t)m->P, sizeof(int));
+    memset(&m->best, 0, sizeof(m->best));
+    memcpy(m->best.genes, initial_guess, n * sizeof(double));
+    m->best.fitness = cost_counted(&m->cx, initial_guess);
+    m->best_curr = m->best;
+    init_population(m, initial_guess);
+}
+
+static void memetic_end(orc_memetic* m) {
+    free(m->pop);
+    free(m->scratch);
+    free(m->order);
+}
+
+/* One pass of the loop body of ik_memetic_impl up to the `terminate` test (ik_memetic.cpp:229-262).
+ * Returns 1 when the species returns its best individual at the solution test. */
+static int memetic_generation(orc_memetic* m, int iter) {
+    const orc_params* p = m->cx.pb->params;
+    for (int i = 0; i < m->E; ++i) gradient_descent(m, i);
+    reproduce(m, (uint32_t)iter);
+    sort_population(m);
+    if (p->stop_optimization_on_valid_solution && orc_is_solution(m->cx.pb, m->best.genes)) return 1;
+    if (check_wipeout(m)) {
+        m->wipeouts++;
+        init_population(m, m->best.genes);
+    }
+    return 0;
+}
+
+/* the tail of ik_memetic_impl (ik_memetic.cpp:272-282) */
+static int memetic_tail_found(const orc_memetic* m) {
+    const orc_params* p = m->cx.pb->params;
+    if (!p->stop_optimization_on_valid_solution && orc_is_solution(m->cx.pb, m->best.genes)) return 1;
+    return p->return_approximate_solution ? 1 : 0;
+}
+
+/* ik_memetic.cpp:285-296 + 211-283, one species */
 void orc_ik_memetic(const orc_problem* pb, const double* initial_guess, uint32_t problem_index,
                     orc_result* out) {
     const orc_params* p = pb->params;
@@ -955,41 +1008,16 @@ void orc_ik_memetic(const orc_problem* pb, const double* initial_guess, uint32_t
         return;
     }
     orc_memetic m;
-    memset(&m, 0, sizeof(m));
-    m.cx.pb = pb;
-    m.n = n;
-    m.P = p->memetic_population_size;
-    m.E = p->memetic_elite_size;
-    m.problem_index = problem_index;
-    m.pop = (orc_individual*)calloc((size_t)m.P, sizeof(orc_individual));
-    m.scratch = (orc_individual*)calloc((size_t)m.P, sizeof(orc_individual));
-    m.order = (int*)calloc((size_t)m.P, sizeof(int));
-
-    /* MemeticIk::from, ik_memetic.cpp:18-41 */
-    memset(&m.best, 0, sizeof(m.best));
-    memcpy(m.best.genes, initial_guess, n * sizeof(double));
-    m.best.fitness = cost_counted(&m.cx, initial_guess);
-    m.best_curr = m.best;
-
-    init_population(&m, initial_guess);
-
+    memetic_begin(&m, pb, initial_guess, problem_index, 0);
     int iter = 0, found = 0;
     while (iter < p->memetic_max_generations) {
-        for (int i = 0; i < m.E; ++i) gradient_descent(&m, i);
-        reproduce(&m, (uint32_t)iter);
-        sort_population(&m);
-        if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, m.best.genes)) {
+        if (memetic_generation(&m, iter)) {
             found = 1;
             break;
         }
-        if (check_wipeout(&m)) {
-            m.wipeouts++;
-            init_population(&m, m.best.genes);
-        }
         iter++;
     }
-    if (!found && !p->stop_optimization_on_valid_solution && orc_is_solution(pb, m.best.genes)) found = 1;
-    if (!found && p->return_approximate_solution) found = 1;
+    if (!found) found = memetic_tail_found(&m);
 
     out->found = found;
     out->iterations = iter;
@@ -998,9 +1026,105 @@ void orc_ik_memetic(const orc_problem* pb, const double* initial_guess, uint32_t
     out->wipeouts = m.wipeouts;
     out->gd_steps = m.cx.gd_steps;
     memcpy(out->solution, m.best.genes, n * sizeof(double));
-    free(m.pop);
-    free(m.scratch);
-    free(m.order);
+    memetic_end(&m);
+}
+
+/* ik_memetic.cpp:285-373 with num_threads species.  The reference races its species in OS threads and takes
+ * their results in the order they arrive, which no test pins; defined here (and in the CUDA product) as the
+ * lockstep schedule: every live species executes generation g before any executes g + 1, and results arrive in
+ * the order (generations executed, returned at the solution test before returned on `terminate`, species
+ * index).  `terminate` (set when the first arrival holds a value and stop_on_first_soln, :334-346) is seen by
+ * the other species at the test that ends the generation in which it was set (:264-268): they leave the loop
+ * before iter++ and return through the tail (:272-282).  A flag set in the last generation is not observed
+ * (the loop ends anyway; only the reported generation count would differ).  The pick (:352-370): the first
+ * arrival, if it holds a value and stop_on_first_soln, unconditionally; then every value whose fitness is
+ * strictly below the current minimum.  Species s draws from the streams of the problem with the individual
+ * word | s << 16.  Without any value: found = 0, the lowest best fitness and the largest generation count. */
+void orc_ik_memetic_species(const orc_problem* pb, const double* initial_guess, uint32_t problem_index,
+                            int n_species, int stop_on_first, orc_result* out) {
+    const orc_params* p = pb->params;
+    const int n = pb->robot->n;
+    const int G = p->memetic_max_generations;
+    memset(out, 0, sizeof(*out));
+    if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, initial_guess)) {
+        out->found = 1;
+        memcpy(out->solution, initial_guess, n * sizeof(double));
+        out->cost = orc_cost(pb, initial_guess);
+        return;
+    }
+    const int S = n_species < 1 ? 1 : n_species;
+    orc_memetic* ms = (orc_memetic*)calloc((size_t)S, sizeof(orc_memetic));
+    int* done = (int*)calloc((size_t)S, sizeof(int));
+    int* found = (int*)calloc((size_t)S, sizeof(int));
+    int* iters = (int*)calloc((size_t)S, sizeof(int));
+    int* phase = (int*)calloc((size_t)S, sizeof(int));
+    for (int s = 0; s < S; ++s) memetic_begin(&ms[s], pb, initial_guess, problem_index, (uint32_t)s);
+    for (int iter = 0; iter < G; ++iter) {
+        int value_this_generation = 0, live = 0;
+        for (int s = 0; s < S; ++s) {
+            if (done[s]) continue;
+            if (memetic_generation(&ms[s], iter)) {
+                done[s] = 1; found[s] = 1; iters[s] = iter; phase[s] = 0;
+                value_this_generation = 1;
+            } else {
+                live++;
+            }
+        }
+        if (stop_on_first && value_this_generation && iter + 1 < G) {
+            for (int s = 0; s < S; ++s) {
+                if (done[s]) continue;
+                done[s] = 1; found[s] = memetic_tail_found(&ms[s]); iters[s] = iter; phase[s] = 1;
+            }
+            live = 0;
+        }
+        if (!live) break;
+    }
+    for (int s = 0; s < S; ++s) {
+        if (done[s]) continue;
+        done[s] = 1; found[s] = memetic_tail_found(&ms[s]); iters[s] = G; phase[s] = 0;
+    }
+    /* arrival order */
+    int pick = -1;
+    double min_cost = 1.7976931348623157e308;
+    int prev_it = -1, prev_ph = -1, prev_s = -1;
+    double fail_cost = 0.0;
+    int fail_it = 0;
+    for (int k = 0; k < S; ++k) {
+        int cur = -1;
+        for (int s = 0; s < S; ++s) {
+            int after_prev = iters[s] > prev_it ||
+                             (iters[s] == prev_it && (phase[s] > prev_ph || (phase[s] == prev_ph && s > prev_s)));
+            int before_cur = cur < 0 || iters[s] < iters[cur] ||
+                             (iters[s] == iters[cur] && (phase[s] < phase[cur] || (phase[s] == phase[cur] && s < cur)));
+            if (after_prev && before_cur) cur = s;
+        }
+        prev_it = iters[cur]; prev_ph = phase[cur]; prev_s = cur;
+        double c = ms[cur].best.fitness;
+        if (k == 0 || fit_less(c, fail_cost)) fail_cost = c;
+        if (iters[cur] > fail_it) fail_it = iters[cur];
+        if (found[cur] && ((k == 0 && stop_on_first) || c < min_cost)) {
+            pick = cur;
+            min_cost = c;
+        }
+    }
+    for (int s = 0; s < S; ++s) {
+        out->evals += ms[s].cx.evals;
+        out->wipeouts += ms[s].wipeouts;
+        out->gd_steps += ms[s].cx.gd_steps;
+    }
+    if (pick >= 0) {
+        out->found = 1;
+        out->iterations = iters[pick];
+        out->cost = ms[pick].best.fitness;
+        memcpy(out->solution, ms[pick].best.genes, n * sizeof(double));
+    } else {
+        out->found = 0;
+        out->iterations = fail_it;
+        out->cost = fail_cost;
+        memcpy(out->solution, initial_guess, n * sizeof(double));
+    }
+    for (int s = 0; s < S; ++s) memetic_end(&ms[s]);
+    free(ms); free(done); free(found); free(iters); free(phase);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1028,7 +1152,10 @@ static void solve_one(batch_job* job, int64_t b, uint64_t* evals) {
     orc_problem pb;
     orc_problem_init(&pb, job->robot, job->params, job->goal_pose + 7 * b, seed);
     orc_result res;
-    if (job->params->mode == 0)
+    if (job->params->mode == 0 && job->params->memetic_num_threads > 1)
+        orc_ik_memetic_species(&pb, seed, (uint32_t)(job->first + b), job->params->memetic_num_threads,
+                               job->params->memetic_stop_on_first_solution, &res);
+    else if (job->params->mode == 0)
         orc_ik_memetic(&pb, seed, (uint32_t)(job->first + b), &res);
     else
         orc_ik_gradient(&pb, seed, &res);

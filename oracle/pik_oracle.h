@@ -14,7 +14,7 @@
  *                                  per-joint-type semantics also follow src/forward_kinematics.cpp:39-80
  *   src/goal.cpp:17-144,163-203    distances, frame tests, pose cost, joint goals, solution test, cost
  *   src/ik_gradient.cpp:14-139     GradientIk::from, step, ik_gradient
- *   src/ik_memetic.cpp:18-283      MemeticIk, ik_memetic_impl, ik_memetic (single species)
+ *   src/ik_memetic.cpp:18-373      MemeticIk, ik_memetic_impl, ik_memetic (one species or several, lockstep)
  *   src/pick_ik_plugin.cpp:88-217  goal assembly, threshold enabling, YAML -> solver param mapping
  *
  * PARITY PINNING.  The reference cannot be built in this environment (needs ROS 2, MoveIt, Eigen,
@@ -110,6 +110,8 @@ typedef struct {
     int32_t memetic_max_generations;
     int32_t memetic_gd_max_iters;
     int32_t return_approximate_solution;
+    int32_t memetic_num_threads;            /* species (ik_memetic.cpp:315-370) */
+    int32_t memetic_stop_on_first_solution;
     uint64_t rng_seed;
 } orc_params;
 
@@ -175,6 +177,9 @@ typedef struct {
 void orc_ik_gradient(const orc_problem* pb, const double* initial_guess, orc_result* out);
 void orc_ik_memetic(const orc_problem* pb, const double* initial_guess, uint32_t problem_index,
                     orc_result* out);
+/* ik_memetic with num_threads species in the lockstep schedule (see pik_oracle.c) */
+void orc_ik_memetic_species(const orc_problem* pb, const double* initial_guess, uint32_t problem_index,
+                            int n_species, int stop_on_first, orc_result* out);
 
 /* Batch driver = plugin mapping (pick_ik_plugin.cpp:209-217): error_code 1 / -31, solution = seed on
  * failure.  seed_stride = 0 broadcasts one seed.  n_threads <= 0: all cores. */

@@ -27,7 +27,7 @@ EXPORTS = [
     "pik_version", "pik_status_string", "pik_params_default", "pik_params_validate", "pik_robot_create",
     "pik_robot_destroy", "pik_robot_num_variables", "pik_robot_get_variable",
     "pik_robot_is_valid_configuration", "pik_robot_chain_signature", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
-    "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
+    "pik_solve_batch_async", "pik_solver_wait", "pik_solver_query", "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
     "pik_device_count", "pik_host_alloc", "pik_host_free", "pik_measure_fp64_peak",
     "pik_urdf_chain", "pik_comm_unique_id", "pik_comm_create", "pik_comm_destroy", "pik_comm_last_error", "pik_solve_batch_sharded",
 ]
@@ -112,6 +112,9 @@ def lib() -> C.CDLL:
     L.pik_solver_destroy.argtypes = [vp]
     L.pik_solve_batch.argtypes = [vp, C.POINTER(Params), C.c_int64, C.c_int64, dp, dp, C.c_int64, dp, ip, dp, ip,
                                   C.c_int32]
+    L.pik_solve_batch_async.argtypes = L.pik_solve_batch.argtypes
+    L.pik_solver_wait.argtypes = [vp]
+    L.pik_solver_query.argtypes = [vp]
     L.pik_eval_cost.argtypes = [vp, C.POINTER(Params), C.c_int64, dp, dp, C.c_int64, dp, dp, ip, dp, C.c_int32]
     L.pik_solver_synchronize.argtypes = [vp]
     L.pik_solver_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -260,6 +263,23 @@ class Solver:
         rc = lib().pik_solve_batch(self.handle, C.byref(params), B, first_problem_index, goal_pose, seed, seed_stride,
                                    solution, error_code, cost or None, iterations or None, memory)
         self._check(rc, "pik_solve_batch")
+
+    def solve_batch_async_ptr(self, params: Params, B: int, first_problem_index: int, goal_pose: int, seed: int,
+                              seed_stride: int, solution: int, error_code: int, cost: int, iterations: int,
+                              memory: int = MEM_DEVICE):
+        """pik_solve_batch_async: enqueue the whole solve on the solver's stream and return; wait() completes it."""
+        rc = lib().pik_solve_batch_async(self.handle, C.byref(params), B, first_problem_index, goal_pose, seed,
+                                         seed_stride, solution, error_code, cost or None, iterations or None, memory)
+        self._check(rc, "pik_solve_batch_async")
+
+    def wait(self):
+        self._check(lib().pik_solver_wait(self.handle), "pik_solver_wait")
+
+    def query(self) -> bool:
+        rc = lib().pik_solver_query(self.handle)
+        if rc < 0:
+            self._check(rc, "pik_solver_query")
+        return rc == 1
 
     def solve_batch_sharded_ptr(self, comm: "Comm", params: Params, B_local: int, first_problem_index: int,
                                 goal_pose: int, seed: int, seed_stride: int, gathered: int, memory: int = MEM_DEVICE):

@@ -4,10 +4,12 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/pik.h"
 #include "pik_host_robot.h"
@@ -35,16 +37,23 @@ struct pik_solver {
     int device = 0;
     int sm_count = 148;
     int spec = 0;  // compiled chain signature matching the robot (select_spec)
+    unsigned short sm_dense[kSmDenseSize];  // %smid -> dense SM index on this device
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-    int32_t* h_counters = nullptr;            // pinned [2]
+    int32_t* h_counters = nullptr;            // pinned [2] (PIK_TRACE only)
     unsigned long long* h_stats = nullptr;    // pinned [4]
     // staging for PIK_MEM_HOST calls
     DeviceArray d_goal, d_seed, d_q, d_solution, d_error, d_cost, d_iters, d_issol, d_tip, d_packed, d_gather;
     // solver state
-    DeviceArray d_pop, d_order, d_hdr, d_meta, d_active, d_counters, d_stats;
+    DeviceArray d_pop, d_order, d_hdr, d_meta, d_active, d_counters, d_sched, d_stats;
+    // per-species results and the terminate flags of a multi-species solve (memetic_num_threads > 1)
+    DeviceArray d_sub_solution, d_sub_error, d_sub_cost, d_sub_iters, d_group_term;
     pik_stats stats{};
+    // the solve in flight between pik_solve_batch_async and pik_solver_wait
+    bool in_flight = false;
+    bool timed_generations = false;
+    int in_flight_status = PIK_OK;
     std::string last_error;
 };
 
@@ -82,34 +91,94 @@ void release(DeviceArray& a) {
 
 bool finite_ge(double v, double lo) { return v == v && v >= lo; }
 
-// The robot table and the solver parameters live in __constant__ memory, one copy per device: calls that
-// launch kernels are serialised per process.
-std::mutex g_launch_mutex;
+// ---------------------------------------------------------------------------------------------------
+// The robot table and the solver parameters are read by the kernels as constant-bank operands of the FP64
+// instructions (c_rb / c_pr, pik_device.cuh): one copy per DEVICE.  Calls on different devices never meet.
+// Calls on the same device SHARE the copy when their robot table and parameters are identical (two solvers
+// pipelining batches on two streams, concurrent searchPositionIK calls of one plugin: the per-call data --
+// buffers, RNG key schedule, species count -- travel as kernel arguments); a call with different contents waits,
+// on the host, for the device work that still reads the old contents, then replaces them.  No lock is held while
+// a solve runs.
+// ---------------------------------------------------------------------------------------------------
+struct DeviceConstants {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool valid = false;
+    DevRobot rb;
+    DevParams pr;
+    int enqueuing = 0;                  // calls between acquire and commit (their launches are being issued)
+    std::vector<cudaEvent_t> readers;   // completion events of committed calls that read the current contents
+    cudaEvent_t uploaded = nullptr;     // recorded behind the last upload
+};
+constexpr int kMaxDevices = 64;
+DeviceConstants g_constants[kMaxDevices];
 
-bool trace_enabled() {
-    static const bool v = std::getenv("PIK_TRACE") != nullptr;
-    return v;
+// Makes (rb, pr) the constants of s->device for the work s is about to enqueue on its stream.
+int constants_acquire(pik_solver* s, const DevRobot& rb, const DevParams& pr) {
+    if (s->device < 0 || s->device >= kMaxDevices) return PIK_E_INVALID_ARGUMENT;
+    DeviceConstants& dc = g_constants[s->device];
+    std::unique_lock<std::mutex> lock(dc.mu);
+    const bool same = dc.valid && std::memcmp(&dc.rb, &rb, sizeof(rb)) == 0 && std::memcmp(&dc.pr, &pr, sizeof(pr)) == 0;
+    if (!same) {
+        dc.cv.wait(lock, [&] { return dc.enqueuing == 0; });
+        for (cudaEvent_t ev : dc.readers) PIK_CUDA(s, cudaEventSynchronize(ev));
+        dc.readers.clear();
+        dc.valid = false;
+        if (!dc.uploaded) PIK_CUDA(s, cudaEventCreateWithFlags(&dc.uploaded, cudaEventDisableTiming));
+        dc.rb = rb;
+        dc.pr = pr;
+        PIK_CUDA(s, upload_constants(s->stream, dc.rb, dc.pr));
+        PIK_CUDA(s, cudaEventRecord(dc.uploaded, s->stream));
+        dc.valid = true;
+    }
+    dc.enqueuing += 1;
+    lock.unlock();
+    // launches on other streams than the uploading one must not overtake the upload
+    const cudaError_t e = cudaStreamWaitEvent(s->stream, dc.uploaded, 0);
+    if (e != cudaSuccess) {
+        lock.lock();
+        dc.enqueuing -= 1;
+        dc.cv.notify_all();
+        return fail_cuda(s, e, "cudaStreamWaitEvent");
+    }
+    return PIK_OK;
 }
 
-// PIK_TRACE_GENERATIONS: one launch per generation even in wide mode (per-generation timing)
+// The call has issued its last launch (done: an event recorded behind it on the call's stream).
+void constants_commit(pik_solver* s, cudaEvent_t done) {
+    DeviceConstants& dc = g_constants[s->device];
+    std::lock_guard<std::mutex> lock(dc.mu);
+    dc.enqueuing -= 1;
+    if (done) {
+        bool present = false;
+        for (cudaEvent_t ev : dc.readers) present = present || ev == done;
+        if (!present) dc.readers.push_back(done);
+    }
+    dc.cv.notify_all();
+}
+
+void constants_forget(pik_solver* s, cudaEvent_t ev) {
+    if (s->device < 0 || s->device >= kMaxDevices) return;
+    DeviceConstants& dc = g_constants[s->device];
+    std::lock_guard<std::mutex> lock(dc.mu);
+    for (size_t i = 0; i < dc.readers.size(); ++i)
+        if (dc.readers[i] == ev) {
+            dc.readers.erase(dc.readers.begin() + (long)i);
+            break;
+        }
+}
+
+bool trace_enabled() { return std::getenv("PIK_TRACE") != nullptr; }
+
+// PIK_TRACE_GENERATIONS: one launch per generation even for a handful of problems (no persistent launch)
 bool trace_each_generation() { return std::getenv("PIK_TRACE_GENERATIONS") != nullptr; }
 
-// Lanes per elite for a generation over n_active problems.  A lone warp of this code issues ~0.2
-// instructions per cycle (dependent FP64 chains: 8-cycle DFMA latency), so an SM sub-partition needs 4-5
-// resident warps to stay busy and a launch with fewer is latency-bound.  Throughput mode (1 lane per elite: a
-// whole GD instance per lane, 32 / E problems per warp) executes the fewest instructions per problem but has
-// the longest serial path per generation; as the batch drains, the warp's lanes are spread over the
-// evaluations of each GD step instead (L lanes per elite): the largest L that still keeps about
-// `warps_per_sm` warps per SM (12 = 3 CTAs of the wide flavour, which runs at 168 registers without spills).  PIK_WIDE_WARPS_PER_SM overrides the target (read per call: the parity tests
-// run both mappings; 0 = always throughput mode, huge = always the widest mapping).
-int lanes_for(int64_t n_active, int E, int sm_count) {
+// PIK_WIDE_WARPS_PER_SM overrides the warps per SM the wide lane mapping aims for (read per call: the parity tests
+// run both mappings; 0 = always throughput mode, huge = always the widest mapping the launch can hold).  12 = 3 CTAs
+// of the wide flavour, which runs at 168 registers without spills.
+long long wide_warps_per_sm() {
     const char* env = std::getenv("PIK_WIDE_WARPS_PER_SM");
-    const int64_t warps_per_sm = env ? std::atoll(env) : (int64_t)12;  // what the wide flavour keeps resident
-    const int64_t capacity_lanes = (int64_t)sm_count * warps_per_sm * 32;
-    const int lmax = memetic_max_lanes_per_elite(E);
-    int L = 1;
-    while (L * 2 <= lmax && n_active * E * (L * 2) <= capacity_lanes) L *= 2;
-    return L;
+    return env ? std::atoll(env) : 12ll;
 }
 
 }  // namespace
@@ -128,6 +197,8 @@ const char* pik_status_string(int status) {
         case PIK_E_NO_DEVICE: return "no CUDA device";
         case PIK_E_OUT_OF_MEMORY: return "out of device memory";
         case PIK_E_UNSUPPORTED: return "unsupported";
+        case PIK_E_NCCL: return "NCCL error (pik_comm_last_error)";
+        case PIK_E_BUSY: return "a solve is in flight on this solver";
         default: return "unknown status";
     }
 }
@@ -290,6 +361,18 @@ int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_
         e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_stats), 4 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = configure_kernels();
+    if (e == cudaSuccess) {
+        // one discovery per device and process
+        static std::mutex mu;
+        static bool known[kMaxDevices];
+        static unsigned short table[kMaxDevices][kSmDenseSize];
+        std::lock_guard<std::mutex> lock(mu);
+        if (device < kMaxDevices && !known[device]) {
+            e = discover_sm_ids(s->stream, s->sm_count, table[device]);
+            known[device] = e == cudaSuccess;
+        }
+        if (e == cudaSuccess && device < kMaxDevices) std::memcpy(s->sm_dense, table[device], sizeof(s->sm_dense));
+    }
     if (e != cudaSuccess) {
         std::fprintf(stderr, "pik_solver_create: %s\n", cudaGetErrorString(e));
         pik_solver_destroy(s);
@@ -303,9 +386,11 @@ void pik_solver_destroy(pik_solver* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->ev1) constants_forget(s, s->ev1);
     DeviceArray* arrays[] = {&s->d_goal, &s->d_seed, &s->d_q, &s->d_solution, &s->d_error, &s->d_cost, &s->d_iters,
                              &s->d_issol, &s->d_tip, &s->d_packed, &s->d_gather, &s->d_pop, &s->d_order, &s->d_hdr, &s->d_meta, &s->d_active,
-                             &s->d_counters, &s->d_stats};
+                             &s->d_counters, &s->d_sched, &s->d_stats, &s->d_sub_solution, &s->d_sub_error, &s->d_sub_cost, &s->d_sub_iters,
+                             &s->d_group_term};
     for (DeviceArray* a : arrays) release(*a);
     if (s->h_counters) cudaFreeHost(s->h_counters);
     if (s->h_stats) cudaFreeHost(s->h_stats);
@@ -321,13 +406,36 @@ void pik_solver_destroy(pik_solver* s) {
 
 namespace {
 
-// The solve behind pik_solve_batch.  keep_on_device: the results stay in the solver's device buffers
-// (d_solution, d_error, d_cost, d_iters) for a follow-up on the same stream (the sharded all-gather) and the
-// output pointers are ignored.
-int solve_core(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
-               const double* goal_pose, const double* seed, int64_t seed_stride, double* solution,
-               int32_t* error_code, double* cost, int32_t* iterations, int32_t memory, bool keep_on_device) {
+// Collects the outcome of the solve in flight: waits for the stream, reads the counters and the event times.
+int finish_solve(pik_solver* s) {
+    if (!s->in_flight) return PIK_OK;
+    s->in_flight = false;
+    if (s->in_flight_status != PIK_OK) return s->in_flight_status;
+    PIK_CUDA(s, cudaSetDevice(s->device));
+    PIK_CUDA(s, cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    PIK_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->stats.device_ms = ms;
+    if (s->timed_generations) {
+        PIK_CUDA(s, cudaEventElapsedTime(&ms, s->ev2, s->ev3));
+        s->stats.generation_ms = ms;
+    }
+    s->stats.problem_generations = (int64_t)s->h_stats[0];
+    s->stats.gd_steps = (int64_t)s->h_stats[1];
+    s->stats.solved = (int64_t)s->h_stats[2];
+    return PIK_OK;
+}
+
+// Enqueues a whole solve on the solver's stream: H2D copies (PIK_MEM_HOST), the init kernel, every generation
+// launch (the kernels size and skip themselves from the device-side counters: nothing is read back in between),
+// the pick over species, the D2H copies.  keep_on_device: the results stay in the solver's device buffers
+// (d_solution, d_error, d_cost, d_iters) for a follow-up on the same stream (the sharded gather) and the output
+// pointers are ignored.
+int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
+                  const double* goal_pose, const double* seed, int64_t seed_stride, double* solution,
+                  int32_t* error_code, double* cost, int32_t* iterations, int32_t memory, bool keep_on_device) {
     if (!s) return PIK_E_INVALID_ARGUMENT;
+    if (s->in_flight) return PIK_E_BUSY;
     s->last_error.clear();
     if (!params || B < 0 || !goal_pose || !seed) return PIK_E_INVALID_ARGUMENT;
     if (!keep_on_device && (!solution || !error_code)) return PIK_E_INVALID_ARGUMENT;
@@ -338,19 +446,28 @@ int solve_core(pik_solver* s, const pik_params* params, int64_t B, int64_t first
         return PIK_E_INVALID_ARGUMENT;
     int rc = pik_params_validate(params);
     if (rc != PIK_OK) return rc;
+    const bool global = params->mode == PIK_MODE_GLOBAL;
+    const int S = global ? params->memetic_num_threads : 1;  // species; ik_gradient has none
+    const int64_t n_sub = B * S;
+    if (n_sub > (int64_t)1 << 30) return PIK_E_INVALID_ARGUMENT;
     std::memset(&s->stats, 0, sizeof(s->stats));
     s->stats.problems = B;
+    s->timed_generations = false;
+    s->in_flight_status = PIK_OK;
     if (B == 0) return PIK_OK;
     PIK_CUDA(s, cudaSetDevice(s->device));
-    const DevParams pr = make_dev_params(*params);
+    DevParams pr = make_dev_params(*params);
     const int P = pr.P;
     const size_t seed_elems = seed_stride ? (size_t)B * n : (size_t)n;
 
     SolveBuffers sb;
     std::memset(&sb, 0, sizeof(sb));
-    sb.B = B;
+    sb.B = n_sub;
     sb.first_problem_index = first_problem_index;
     sb.seed_stride = seed_stride;
+    sb.n_species = S;
+    sb.stop_on_first = params->memetic_stop_on_first_solution ? 1 : 0;
+    make_round_keys(params->rng_seed, sb.round_key);
     if (memory == PIK_MEM_HOST) {
         if ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8))) return rc;
         sb.goal_pose = static_cast<double*>(s->d_goal.ptr);
@@ -359,98 +476,141 @@ int solve_core(pik_solver* s, const pik_params* params, int64_t B, int64_t first
         sb.goal_pose = goal_pose;
         sb.seed = seed;
     }
+    // where the per-problem results go on the device
+    double* r_solution = solution;
+    int32_t* r_error = error_code;
+    double* r_cost = cost;
+    int32_t* r_iters = iterations;
     if (memory == PIK_MEM_HOST || keep_on_device) {
         if ((rc = ensure(s, s->d_solution, (size_t)B * n * 8)) || (rc = ensure(s, s->d_error, (size_t)B * 4)) ||
             (rc = ensure(s, s->d_cost, (size_t)B * 8)) || (rc = ensure(s, s->d_iters, (size_t)B * 4)))
             return rc;
-        sb.solution = static_cast<double*>(s->d_solution.ptr);
-        sb.error_code = static_cast<int32_t*>(s->d_error.ptr);
-        sb.cost = static_cast<double*>(s->d_cost.ptr);
-        sb.iterations = static_cast<int32_t*>(s->d_iters.ptr);
+        r_solution = static_cast<double*>(s->d_solution.ptr);
+        r_error = static_cast<int32_t*>(s->d_error.ptr);
+        r_cost = static_cast<double*>(s->d_cost.ptr);
+        r_iters = static_cast<int32_t*>(s->d_iters.ptr);
+    }
+    if (S > 1) {
+        // the kernels write per-species results; species_pick_kernel reduces them to the per-problem results
+        if ((rc = ensure(s, s->d_sub_solution, (size_t)n_sub * n * 8)) || (rc = ensure(s, s->d_sub_error, (size_t)n_sub * 4)) ||
+            (rc = ensure(s, s->d_sub_cost, (size_t)n_sub * 8)) || (rc = ensure(s, s->d_sub_iters, (size_t)n_sub * 4)) ||
+            (rc = ensure(s, s->d_group_term, (size_t)B * 4)))
+            return rc;
+        sb.solution = static_cast<double*>(s->d_sub_solution.ptr);
+        sb.error_code = static_cast<int32_t*>(s->d_sub_error.ptr);
+        sb.cost = static_cast<double*>(s->d_sub_cost.ptr);
+        sb.iterations = static_cast<int32_t*>(s->d_sub_iters.ptr);
+        sb.group_term = static_cast<int32_t*>(s->d_group_term.ptr);
     } else {
-        sb.solution = solution;
-        sb.error_code = error_code;
-        sb.cost = cost;
-        sb.iterations = iterations;
+        sb.solution = r_solution;
+        sb.error_code = r_error;
+        sb.cost = r_cost;
+        sb.iterations = r_iters;
     }
     if ((rc = ensure(s, s->d_stats, 4 * sizeof(unsigned long long)))) return rc;
     sb.stats = static_cast<unsigned long long*>(s->d_stats.ptr);
-    const bool global = params->mode == PIK_MODE_GLOBAL;
+    GenerationPlan plan;
+    std::memset(&plan, 0, sizeof(plan));
+    const size_t n_counters = (size_t)pr.max_generations + 2;
+    const size_t n_sched = ((size_t)pr.max_generations + 1) * ((size_t)s->sm_count + 1);
     if (global) {
         const size_t F = 2 * (size_t)n + 2;
-        if ((rc = ensure(s, s->d_pop, 2 * (size_t)B * F * P * 8)) || (rc = ensure(s, s->d_order, 2 * (size_t)B * P * 2)) ||
-            (rc = ensure(s, s->d_hdr, (size_t)B * (n + 2) * 8)) || (rc = ensure(s, s->d_meta, (size_t)B * sizeof(ProblemMeta))) ||
-            (rc = ensure(s, s->d_active, 2 * (size_t)B * 4)) || (rc = ensure(s, s->d_counters, 2 * 4)))
+        if ((rc = ensure(s, s->d_pop, 2 * (size_t)n_sub * F * P * 8)) || (rc = ensure(s, s->d_order, 2 * (size_t)n_sub * P * 2)) ||
+            (rc = ensure(s, s->d_hdr, (size_t)n_sub * (n + 2) * 8)) || (rc = ensure(s, s->d_meta, (size_t)n_sub * sizeof(ProblemMeta))) ||
+            (rc = ensure(s, s->d_active, 2 * (size_t)n_sub * 4)) || (rc = ensure(s, s->d_counters, n_counters * 4)) ||
+            (rc = ensure(s, s->d_sched, n_sched * 4)))
             return rc;
+        sb.sched = static_cast<int32_t*>(s->d_sched.ptr);
         sb.pop = static_cast<double*>(s->d_pop.ptr);
         sb.order = static_cast<uint16_t*>(s->d_order.ptr);
         sb.hdr = static_cast<double*>(s->d_hdr.ptr);
         sb.meta = static_cast<ProblemMeta*>(s->d_meta.ptr);
         sb.active = static_cast<int32_t*>(s->d_active.ptr);
         sb.counters = static_cast<int32_t*>(s->d_counters.ptr);
+        plan = plan_generations(n, P, pr.E, n_sub, s->sm_count, wide_warps_per_sm(), !trace_each_generation());
+        pr.sm_count = s->sm_count;
+        pr.lanes_max = plan.lanes_max;
+        pr.wide_capacity_lanes = plan.wide_capacity_lanes;
+        pr.wide_units_max = plan.wide_units_max;
+        pr.persistent_units_max = plan.persistent_units_max;
+        std::memcpy(pr.sm_dense, s->sm_dense, sizeof(pr.sm_dense));
     }
 
     cudaStream_t st = s->stream;
-    std::lock_guard<std::mutex> lock(g_launch_mutex);
-    PIK_CUDA(s, cudaEventRecord(s->ev0, st));
-    PIK_CUDA(s, upload_constants(st, s->robot.dev, pr));
-    if (memory == PIK_MEM_HOST) {
-        PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
-        PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
-    }
-    PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 4 * sizeof(unsigned long long), st));
-    if (!global) {
-        PIK_CUDA(s, launch_gd_local(st, s->spec, n, sb));
-        s->stats.kernel_launches += 1;
-    } else {
-        PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, 2 * sizeof(int32_t), st));
-        PIK_CUDA(s, launch_memetic_init(st, s->spec, n, P, pr.E, sb));
-        s->stats.kernel_launches += 1;
-        PIK_CUDA(s, cudaMemcpyAsync(s->h_counters, sb.counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        PIK_CUDA(s, cudaStreamSynchronize(st));
-        int64_t n_active = s->h_counters[0];
-        int list = 0;
-        for (int gen = 0; gen < pr.max_generations && n_active > 0; ++gen) {
-            PIK_CUDA(s, cudaMemsetAsync(sb.counters + (list ^ 1), 0, sizeof(int32_t), st));
-            PIK_CUDA(s, cudaEventRecord(s->ev2, st));
-            const int lanes = lanes_for(n_active, pr.E, s->sm_count);
-            // a launch with one problem per warp runs every remaining generation of its problems
-            // (only once every warp has an SM sub-partition to itself: a launch per generation re-spreads the
-            // survivors over the SMs, a persistent warp stays where it started)
-            const bool persistent = memetic_shape(n, P, pr.E, lanes).problems_per_warp == 1 &&
-                                    n_active <= (int64_t)s->sm_count * 4 && !trace_each_generation();
-            const int max_gens = persistent ? pr.max_generations - gen : 1;
-            PIK_CUDA(s, launch_memetic_generation(st, s->spec, n, P, pr.E, sb, list, n_active, lanes, max_gens));
-            PIK_CUDA(s, cudaEventRecord(s->ev3, st));
-            s->stats.kernel_launches += 1;
-            s->stats.generation_launches += 1;
-            PIK_CUDA(s, cudaMemcpyAsync(s->h_counters + (list ^ 1), sb.counters + (list ^ 1), sizeof(int32_t),
-                                        cudaMemcpyDeviceToHost, st));
-            PIK_CUDA(s, cudaStreamSynchronize(st));
-            float gms = 0.f;
-            PIK_CUDA(s, cudaEventElapsedTime(&gms, s->ev2, s->ev3));
-            s->stats.generation_ms += gms;
-            if (trace_enabled())
-                std::fprintf(stderr, "pik gen %3d active %8lld lanes %2d  %8.3f ms\n", gen, (long long)n_active, lanes, gms);
-            n_active = s->h_counters[list ^ 1];
-            list ^= 1;
+    if ((rc = constants_acquire(s, s->robot.dev, pr)) != PIK_OK) return rc;
+    // from here on every exit goes through constants_commit
+    auto issue = [&]() -> int {
+        PIK_CUDA(s, cudaEventRecord(s->ev0, st));
+        if (memory == PIK_MEM_HOST) {
+            PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
+            PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
         }
+        PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 4 * sizeof(unsigned long long), st));
+        if (!global) {
+            PIK_CUDA(s, launch_gd_local(st, s->spec, n, sb));
+            s->stats.kernel_launches += 1;
+        } else {
+            PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, n_counters * sizeof(int32_t), st));
+            PIK_CUDA(s, cudaMemsetAsync(sb.sched, 0, n_sched * sizeof(int32_t), st));
+            if (sb.group_term) PIK_CUDA(s, cudaMemsetAsync(sb.group_term, 0, (size_t)B * sizeof(int32_t), st));
+            PIK_CUDA(s, launch_memetic_init(st, s->spec, n, P, pr.E, sb));
+            s->stats.kernel_launches += 1;
+            PIK_CUDA(s, cudaEventRecord(s->ev2, st));
+            const bool trace = trace_enabled();
+            const int n_gens = plan.first_launch_runs_all ? 1 : pr.max_generations;
+            for (int gen = 0; gen < n_gens; ++gen) {
+                if (trace) PIK_CUDA(s, cudaEventRecord(s->ev2, st));
+                if (plan.use_throughput) {
+                    PIK_CUDA(s, launch_memetic_generation(st, s->spec, plan, sb, gen, false));
+                    s->stats.kernel_launches += 1;
+                }
+                if (plan.use_wide) {
+                    PIK_CUDA(s, launch_memetic_generation(st, s->spec, plan, sb, gen, true));
+                    s->stats.kernel_launches += 1;
+                }
+                s->stats.generation_launches += 1;
+                if (trace) {
+                    // PIK_TRACE: host-synchronous, one line per generation (experiments only)
+                    PIK_CUDA(s, cudaEventRecord(s->ev3, st));
+                    PIK_CUDA(s, cudaMemcpyAsync(s->h_counters, sb.counters + gen, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                    PIK_CUDA(s, cudaStreamSynchronize(st));
+                    float gms = 0.f;
+                    PIK_CUDA(s, cudaEventElapsedTime(&gms, s->ev2, s->ev3));
+                    s->stats.generation_ms += gms;
+                    const int n_active = s->h_counters[0];
+                    std::fprintf(stderr, "pik gen %3d active %8d lanes %2d  %8.3f ms\n", gen, n_active,
+                                 lanes_for(n_active, pr.E, pr.lanes_max, pr.wide_capacity_lanes, pr.wide_units_max), gms);
+                    if (s->h_counters[1] == 0) break;
+                }
+            }
+            if (!trace) {
+                PIK_CUDA(s, cudaEventRecord(s->ev3, st));
+                s->timed_generations = true;
+            }
+            if (S > 1) {
+                PIK_CUDA(s, launch_species_pick(st, sb, n, B, r_solution, r_error, r_cost, r_iters));
+                s->stats.kernel_launches += 1;
+            }
+        }
+        if (memory == PIK_MEM_HOST && !keep_on_device) {
+            PIK_CUDA(s, cudaMemcpyAsync(solution, r_solution, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));
+            PIK_CUDA(s, cudaMemcpyAsync(error_code, r_error, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+            if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, r_cost, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+            if (iterations) PIK_CUDA(s, cudaMemcpyAsync(iterations, r_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        }
+        PIK_CUDA(s, cudaMemcpyAsync(s->h_stats, sb.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        PIK_CUDA(s, cudaEventRecord(s->ev1, st));
+        return PIK_OK;
+    };
+    rc = issue();
+    if (rc != PIK_OK) {
+        // kernels already issued may still read the constants: drain the stream before anyone replaces them
+        cudaStreamSynchronize(st);
+        constants_commit(s, nullptr);
+        return rc;
     }
-    if (memory == PIK_MEM_HOST && !keep_on_device) {
-        PIK_CUDA(s, cudaMemcpyAsync(solution, sb.solution, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));
-        PIK_CUDA(s, cudaMemcpyAsync(error_code, sb.error_code, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-        if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, sb.cost, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-        if (iterations) PIK_CUDA(s, cudaMemcpyAsync(iterations, sb.iterations, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    }
-    PIK_CUDA(s, cudaMemcpyAsync(s->h_stats, sb.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    PIK_CUDA(s, cudaEventRecord(s->ev1, st));
-    PIK_CUDA(s, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    PIK_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    s->stats.device_ms = ms;
-    s->stats.problem_generations = (int64_t)s->h_stats[0];
-    s->stats.gd_steps = (int64_t)s->h_stats[1];
-    s->stats.solved = (int64_t)s->h_stats[2];
+    constants_commit(s, s->ev1);
+    s->in_flight = true;
     return PIK_OK;
 }
 
@@ -458,17 +618,42 @@ int solve_core(pik_solver* s, const pik_params* params, int64_t B, int64_t first
 
 extern "C" {
 
+int pik_solve_batch_async(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
+                          const double* goal_pose, const double* seed, int64_t seed_stride, double* solution,
+                          int32_t* error_code, double* cost, int32_t* iterations, int32_t memory) {
+    return enqueue_solve(s, params, B, first_problem_index, goal_pose, seed, seed_stride, solution, error_code, cost,
+                         iterations, memory, false);
+}
+
+int pik_solver_wait(pik_solver* s) {
+    if (!s) return PIK_E_INVALID_ARGUMENT;
+    return finish_solve(s);
+}
+
+int pik_solver_query(pik_solver* s) {
+    if (!s) return PIK_E_INVALID_ARGUMENT;
+    if (!s->in_flight) return 1;
+    if (cudaSetDevice(s->device) != cudaSuccess) return PIK_E_CUDA;
+    const cudaError_t e = cudaEventQuery(s->ev1);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    return fail_cuda(s, e, "cudaEventQuery");
+}
+
 int pik_solve_batch(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
                     const double* goal_pose, const double* seed, int64_t seed_stride, double* solution,
                     int32_t* error_code, double* cost, int32_t* iterations, int32_t memory) {
-    return solve_core(s, params, B, first_problem_index, goal_pose, seed, seed_stride, solution, error_code, cost,
-                      iterations, memory, false);
+    const int rc = enqueue_solve(s, params, B, first_problem_index, goal_pose, seed, seed_stride, solution, error_code,
+                                 cost, iterations, memory, false);
+    if (rc != PIK_OK) return rc;
+    return finish_solve(s);
 }
 
 int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const double* goal_pose, const double* seed,
                   int64_t seed_stride, const double* q, double* cost, int32_t* is_solution, double* tip_pose,
                   int32_t memory) {
     if (!s) return PIK_E_INVALID_ARGUMENT;
+    if (s->in_flight) return PIK_E_BUSY;
     s->last_error.clear();
     if (!params || B < 0 || !goal_pose || !seed || !q) return PIK_E_INVALID_ARGUMENT;
     const int n = s->robot.dev.n;
@@ -480,30 +665,37 @@ int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const doub
     PIK_CUDA(s, cudaSetDevice(s->device));
     const DevParams pr = make_dev_params(*params);
     cudaStream_t st = s->stream;
-    std::lock_guard<std::mutex> lock(g_launch_mutex);
-    PIK_CUDA(s, upload_constants(st, s->robot.dev, pr));
-    if (memory == PIK_MEM_DEVICE) {
-        PIK_CUDA(s, launch_eval_cost(st, n, B, goal_pose, seed, seed_stride, q, cost, is_solution, tip_pose));
-        PIK_CUDA(s, cudaStreamSynchronize(st));
-        return PIK_OK;
-    }
     const size_t seed_elems = seed_stride ? (size_t)B * n : (size_t)n;
-    if ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8)) ||
-        (rc = ensure(s, s->d_q, (size_t)B * n * 8)) || (rc = ensure(s, s->d_cost, (size_t)B * 8)) ||
-        (rc = ensure(s, s->d_issol, (size_t)B * 4)) || (rc = ensure(s, s->d_tip, (size_t)B * 7 * 8)))
+    if (memory == PIK_MEM_HOST &&
+        ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8)) ||
+         (rc = ensure(s, s->d_q, (size_t)B * n * 8)) || (rc = ensure(s, s->d_cost, (size_t)B * 8)) ||
+         (rc = ensure(s, s->d_issol, (size_t)B * 4)) || (rc = ensure(s, s->d_tip, (size_t)B * 7 * 8))))
         return rc;
-    PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
-    PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
-    PIK_CUDA(s, cudaMemcpyAsync(s->d_q.ptr, q, (size_t)B * n * 8, cudaMemcpyHostToDevice, st));
-    PIK_CUDA(s, launch_eval_cost(st, n, B, static_cast<double*>(s->d_goal.ptr),
-                                 static_cast<double*>(s->d_seed.ptr), seed_stride, static_cast<double*>(s->d_q.ptr),
-                                 cost ? static_cast<double*>(s->d_cost.ptr) : nullptr,
-                                 is_solution ? static_cast<int32_t*>(s->d_issol.ptr) : nullptr,
-                                 tip_pose ? static_cast<double*>(s->d_tip.ptr) : nullptr));
-    if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, s->d_cost.ptr, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-    if (is_solution) PIK_CUDA(s, cudaMemcpyAsync(is_solution, s->d_issol.ptr, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    if (tip_pose) PIK_CUDA(s, cudaMemcpyAsync(tip_pose, s->d_tip.ptr, (size_t)B * 7 * 8, cudaMemcpyDeviceToHost, st));
-    PIK_CUDA(s, cudaStreamSynchronize(st));
+    if ((rc = constants_acquire(s, s->robot.dev, pr)) != PIK_OK) return rc;
+    auto issue = [&]() -> int {
+        if (memory == PIK_MEM_DEVICE) {
+            PIK_CUDA(s, launch_eval_cost(st, n, B, goal_pose, seed, seed_stride, q, cost, is_solution, tip_pose));
+            return PIK_OK;
+        }
+        PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
+        PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
+        PIK_CUDA(s, cudaMemcpyAsync(s->d_q.ptr, q, (size_t)B * n * 8, cudaMemcpyHostToDevice, st));
+        PIK_CUDA(s, launch_eval_cost(st, n, B, static_cast<double*>(s->d_goal.ptr),
+                                     static_cast<double*>(s->d_seed.ptr), seed_stride, static_cast<double*>(s->d_q.ptr),
+                                     cost ? static_cast<double*>(s->d_cost.ptr) : nullptr,
+                                     is_solution ? static_cast<int32_t*>(s->d_issol.ptr) : nullptr,
+                                     tip_pose ? static_cast<double*>(s->d_tip.ptr) : nullptr));
+        if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, s->d_cost.ptr, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+        if (is_solution) PIK_CUDA(s, cudaMemcpyAsync(is_solution, s->d_issol.ptr, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        if (tip_pose) PIK_CUDA(s, cudaMemcpyAsync(tip_pose, s->d_tip.ptr, (size_t)B * 7 * 8, cudaMemcpyDeviceToHost, st));
+        return PIK_OK;
+    };
+    rc = issue();
+    // the call is synchronous: no reader is left behind when it returns
+    const cudaError_t e = cudaStreamSynchronize(st);
+    constants_commit(s, nullptr);
+    if (rc != PIK_OK) return rc;
+    if (e != cudaSuccess) return fail_cuda(s, e, "cudaStreamSynchronize");
     return PIK_OK;
 }
 
@@ -535,6 +727,7 @@ void pik_host_free(void* p) {
 
 int pik_measure_fp64_peak(pik_solver* s, double* tflops) {
     if (!s || !tflops) return PIK_E_INVALID_ARGUMENT;
+    if (s->in_flight) return PIK_E_BUSY;
     PIK_CUDA(s, cudaSetDevice(s->device));
     cudaDeviceProp prop;
     PIK_CUDA(s, cudaGetDeviceProperties(&prop, s->device));
@@ -566,9 +759,11 @@ void* pik_internal_solver_stream(const pik_solver* s) { return s ? static_cast<v
 
 int pik_internal_solve_keep(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
                             const double* goal_pose, const double* seed, int64_t seed_stride, int32_t memory) {
-    return solve_core(s, params, B, first_problem_index, goal_pose, seed, seed_stride, nullptr, nullptr, nullptr, nullptr,
-                      memory, true);
+    return enqueue_solve(s, params, B, first_problem_index, goal_pose, seed, seed_stride, nullptr, nullptr, nullptr, nullptr,
+                         memory, true);
 }
+
+int pik_internal_finish(pik_solver* s) { return s ? finish_solve(s) : PIK_E_INVALID_ARGUMENT; }
 
 int pik_internal_pack(pik_solver* s, int64_t B, size_t packed_elems, size_t gather_elems, double** packed, double** gather) {
     if (!s || !packed || !gather) return PIK_E_INVALID_ARGUMENT;

@@ -145,22 +145,30 @@ int pik_solve_batch_sharded(pik_solver* solver, pik_comm* comm, const pik_params
     if (!api) return PIK_E_NCCL;
     int rc = pik_internal_solve_keep(solver, params, B_local, first_problem_index, goal_pose, seed, seed_stride, memory);
     if (rc != PIK_OK || B_local == 0) return rc;
+    // the solve is enqueued; the pack and the collective go behind it on the same stream
     const int n = pik_internal_solver_num_variables(solver);
     const size_t row = (size_t)B_local * (size_t)(n + 3);
     double* packed = nullptr;
     double* dst = nullptr;
     // packed shard and (for host callers) the gathered block live in the solver's staging buffers
     rc = pik_internal_pack(solver, B_local, row, memory == PIK_MEM_HOST ? row * (size_t)comm->n_ranks : 0, &packed, &dst);
-    if (rc != PIK_OK) return rc;
+    if (rc != PIK_OK) {
+        pik_internal_finish(solver);
+        return rc;
+    }
     if (memory == PIK_MEM_DEVICE) dst = gathered;
     cudaStream_t st = static_cast<cudaStream_t>(pik_internal_solver_stream(solver));
     const ncclResult_t r = api->AllGather(packed, dst, row, ncclDouble, comm->comm, st);
-    if (r != ncclSuccess) return fail_nccl(api, r, "ncclAllGather");
+    if (r != ncclSuccess) {
+        pik_internal_finish(solver);
+        return fail_nccl(api, r, "ncclAllGather");
+    }
     if (memory == PIK_MEM_HOST &&
-        cudaMemcpyAsync(gathered, dst, row * (size_t)comm->n_ranks * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        cudaMemcpyAsync(gathered, dst, row * (size_t)comm->n_ranks * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        pik_internal_finish(solver);
         return PIK_E_CUDA;
-    if (cudaStreamSynchronize(st) != cudaSuccess) return PIK_E_CUDA;
-    return PIK_OK;
+    }
+    return pik_internal_finish(solver);
 }
 
 }  // extern "C"

@@ -154,15 +154,18 @@ inline DevParams make_dev_params(const pik_params& p) {
     d.P = p.memetic_population_size;
     d.E = p.memetic_elite_size;
     d.max_generations = p.memetic_max_generations;
-    d.seed_lo = static_cast<uint32_t>(p.rng_seed);
-    d.seed_hi = static_cast<uint32_t>(p.rng_seed >> 32);
-    for (int r = 0; r < 10; ++r) {
-        d.round_key[2 * r] = d.seed_lo + 0x9E3779B9u * static_cast<uint32_t>(r);
-        d.round_key[2 * r + 1] = d.seed_hi + 0xBB67AE85u * static_cast<uint32_t>(r);
-    }
     d.debug = std::getenv("PIK_DEBUG_PHASES") ? 1 : 0;
     d.lockstep = std::getenv("PIK_NO_LOCKSTEP") ? 0 : (std::getenv("PIK_LOCKSTEP_MASK") ? std::atoi(std::getenv("PIK_LOCKSTEP_MASK")) : 3);
     return d;
+}
+
+// Philox4x32-10 key schedule of rng_seed (travels in the kernel parameter block, SolveBuffers::round_key)
+inline void make_round_keys(uint64_t rng_seed, uint32_t* round_key) {
+    const uint32_t lo = static_cast<uint32_t>(rng_seed), hi = static_cast<uint32_t>(rng_seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        round_key[2 * r] = lo + 0x9E3779B9u * static_cast<uint32_t>(r);
+        round_key[2 * r + 1] = hi + 0xBB67AE85u * static_cast<uint32_t>(r);
+    }
 }
 
 }  // namespace pik

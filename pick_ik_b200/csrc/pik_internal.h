@@ -9,7 +9,8 @@
 int pik_internal_solver_device(const pik_solver* s);
 int pik_internal_solver_num_variables(const pik_solver* s);
 void* pik_internal_solver_stream(const pik_solver* s);
-// pik_solve_batch whose results stay in the solver's device buffers
+// pik_solve_batch_async whose results stay in the solver's device buffers; pik_internal_finish = pik_solver_wait
+int pik_internal_finish(pik_solver* s);
 int pik_internal_solve_keep(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
                             const double* goal_pose, const double* seed, int64_t seed_stride, int32_t memory);
 // packs those results into [B][n + 3] doubles (device, solver-owned); gather_elems > 0 also reserves a

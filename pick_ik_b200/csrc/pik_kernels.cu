@@ -103,6 +103,14 @@ __device__ __forceinline__ uint16_t* order_ptr(const SolveBuffers& sb, int buf, 
     return sb.order + ((size_t)buf * (size_t)sb.B + (size_t)b) * (size_t)P;
 }
 
+// sub-problem sp -> IK problem (goal, seed, RNG problem word) and species (RNG individual word)
+__device__ __forceinline__ int problem_of(const SolveBuffers& sb, int64_t sp) {
+    return sb.n_species == 1 ? (int)sp : (int)(sp / sb.n_species);
+}
+__device__ __forceinline__ uint32_t species_of(const SolveBuffers& sb, int64_t sp) {
+    return sb.n_species == 1 ? 0u : (uint32_t)(sp % sb.n_species);
+}
+
 // Plugin output mapping (src/pick_ik_plugin.cpp:209-217): genes on success, the seed otherwise.
 __device__ __forceinline__ void write_result(const SolveBuffers& sb, int n, int64_t b, bool found, const double* genes,
                                              int genes_stride, const double* seed, double cost, int iterations) {
@@ -236,11 +244,11 @@ __device__ __forceinline__ void init_population_warp(const SolveBuffers& sb, con
         for (int j = 0; j < n; ++j) col[j * kS] = hdr[j];
         double f = hdr[n];
         if (e > 0) {
-            const Stream st = make_stream((uint32_t)(sb.first_problem_index + b), kStreamInit, (uint32_t)m.init_epoch,
-                                          (uint32_t)e);
-            random_valid_configuration(st, col);
+            const Stream st = make_stream((uint32_t)(sb.first_problem_index + problem_of(sb, b)), kStreamInit,
+                                          (uint32_t)m.init_epoch, (uint32_t)e, species_of(sb, b));
+            random_valid_configuration(sb, st, col);
             f = eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k_e,
-                           sb.seed + b * sb.seed_stride, nullptr);
+                           sb.seed + problem_of(sb, b) * sb.seed_stride, nullptr);
         }
         W.efit[lane] = f;
         for (int j = 0; j < n; ++j) {
@@ -291,9 +299,10 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
         W.pidx[lane] = b < sb.B ? (int)b : -1;
         W.flag[lane] = 0;
         if (b < sb.B) {
-            const double* sd = sb.seed + b * sb.seed_stride;
+            const int pb = problem_of(sb, b);
+            const double* sd = sb.seed + pb * sb.seed_stride;
             double* g7 = W.goal + 7 * lane;
-            goal_from_pose(sb.goal_pose + 7 * b, g7);
+            goal_from_pose(sb.goal_pose + 7 * (size_t)pb, g7);
             double* col = W.q + lane;
             double* hdr = sb.hdr + (size_t)b * (n + 2);
             for (int j = 0; j < n; ++j) {
@@ -336,6 +345,37 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
     }
     __syncwarp();
     init_population_warp<S>(sb, W, PW, lane);
+}
+
+// A species that sees `terminate` (src/ik_memetic.cpp:264-282): it has completed its generation, leaves the loop
+// before iter++ and returns its best individual if that passes the solution test (only looked at when the
+// optimisation does not stop on valid solutions) or approximate solutions are allowed.  One lane.
+template <class S>
+__device__ __forceinline__ void finish_terminated(const SolveBuffers& sb, const WarpSmem& W, int b, int lane) {
+    const int n = c_rb.n;
+    ProblemMeta m = sb.meta[b];
+    const int pb = problem_of(sb, b);
+    const double* sd = sb.seed + (size_t)pb * sb.seed_stride;
+    const double* hdr = sb.hdr + (size_t)b * (n + 2);
+    bool found = false;
+    if (!c_pr.stop_on_valid) {
+        double* g7 = W.goal + 7 * lane;
+        goal_from_pose(sb.goal_pose + 7 * (size_t)pb, g7);
+        double* col = W.q + lane;
+        for (int j = 0; j < n; ++j) col[j * kS] = hdr[j];
+        double aux[5];
+        eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
+        found = solution_from_aux(aux);
+    }
+    if (!found && c_pr.approx) found = true;
+    m.status = found ? kSolvedTerminated : kFailedTerminated;
+    m.iter = m.iter - 1;
+    write_result(sb, n, b, found, hdr, 1, sd, hdr[n], m.iter);
+    if (sb.stats) {
+        if (found) atomicAdd(&sb.stats[2], 1ull);
+        atomicAdd(&sb.stats[3], 1ull);
+    }
+    sb.meta[b] = m;
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -462,38 +502,119 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
 // 8 warps per SM at 128 registers; the wide flavour (several lanes per elite) 3 CTAs of 4 warps at 168 registers
 // (no spills: a lone warp pays the full latency of every local-memory access).
 //
-// max_gens: generations this launch may run per problem.  Throughput launches run one (the host compacts the
-// active list between launches).  A launch with one problem per warp (PW == 1) may run many: the warp keeps
-// its problem until it is solved, has failed or has used its budget -- problems are independent, so the tail
-// of the batch needs no global step between generations and the hardware block scheduler balances the load.
+// Launch policy, evaluated on the device: the host enqueues, for every generation g, one launch of the throughput
+// flavour and one of the wide flavour -- each a grid of RESIDENT CTAs (2 resp. 3 per SM) -- and never reads a count
+// back.  Each launch reads the size of generation g's active list, derives the lane mapping from it (lanes_for, the
+// function the host used to call) and returns at once unless the mapping is its own.
+//
+// Work distribution.  The work units (a warp's PW problems) are dealt round-robin into one queue per SM (unit u ->
+// queue u mod n_sm); a CTA claims, one warp-load at a time, from the queue of the SM it RUNS ON (%smid through the
+// dense table sm_dense), so that every SM receives the same number of warps whatever the size of the list and
+// wherever the hardware placed the CTAs -- what used to be a host-side choice of grid and CTA size.  A CTA that has
+// worked and finds its queue empty takes from the other SMs' queues (the tail of a launch of several rounds
+// balances like the hardware's own CTA scheduling); one that finds its queue empty at once leaves (the launch fills
+// less than a wave and the other queues belong to CTAs that are just starting), and the last CTA to leave sweeps up
+// whatever no SM-local CTA has taken (possible only when other kernels occupy part of the device).
+//
+// A wide launch with one problem per warp and at most persistent_units_max problems keeps every problem for all
+// its remaining generations: problems are independent, so the tail of the batch needs no global step between
+// generations; the launches enqueued behind it find an empty list.
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+__device__ __forceinline__ unsigned sm_id() {
+    unsigned v;
+    asm("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
+
 template <class S>
 __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
-                                                                      int list_in, int L, int PW, int max_gens) {
+                                                                      int gen) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_claim[4];
+    const int n_active = sb.counters[gen];
+    if (n_active <= 0) return;
     const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
+    const int L = lanes_for(n_active, E, c_pr.lanes_max, c_pr.wide_capacity_lanes, c_pr.wide_units_max);
+    if ((L > 1) != S::kWide) return;
+    const int PW = 32 / (E * L);
+    const int list_in = gen & 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_active = sb.counters[list_in];
-    const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * PW;
+    const int wpb = blockDim.x >> 5;
+    const int units = (n_active + PW - 1) / PW;
+    const int nsm = c_pr.sm_count;
+    const int sigma = c_pr.sm_dense[sm_id() & (kSmDenseSize - 1)];
+    int* qhead = sb.sched + (size_t)gen * (size_t)(nsm + 1);  // [nsm] queue heads, then the count of CTAs that left
+    const bool persistent = S::kWide && PW == 1 && units <= c_pr.persistent_units_max && !(sb.group_term && sb.stop_on_first);
+    const int max_gens = persistent ? c_pr.max_generations - gen : 1;
     // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
     // GD step (below): warps that run the same code at the same time share their instruction-cache fills.
     const bool lockstep = L == 1 && (c_pr.lockstep & 1) != 0;
     const bool lockstep_rep = L == 1 && (c_pr.lockstep & 2) != 0;
+    const int pw_carve = S::kWide ? wide_problems_per_warp_max(E) : PW;
+    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, pw_carve), n, P, pw_carve);
+    const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;
+    int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
+    bool worked = false, sweeping = false;
+  for (;;) {
+    if (threadIdx.x == 0) {
+        // entries of queue t: units t, t + nsm, t + 2 nsm, ...
+        auto queue_len = [&](int t) { return t < units ? (units - t + nsm - 1) / nsm : 0; };
+        int got_q = -1, got_e = 0, got_n = 0;
+        auto try_queue = [&](int t) {
+            const int ql = queue_len(t);
+            if (ql > 0 && ld_volatile(&qhead[t]) < ql) {
+                const int old = atomicAdd(&qhead[t], wpb);
+                if (old < ql) {
+                    got_q = t;
+                    got_e = old;
+                    got_n = ql - old < wpb ? ql - old : wpb;
+                }
+            }
+        };
+        try_queue(sigma);
+        if (got_q < 0 && (worked || sweeping))
+            for (int d = 1; d < nsm && got_q < 0; ++d) try_queue(sigma + d < nsm ? sigma + d : sigma + d - nsm);
+        s_claim[0] = got_q;
+        s_claim[1] = got_e;
+        s_claim[2] = got_n;
+    }
+    __syncthreads();
+    const int claim_q = s_claim[0], claim_e = s_claim[1], claim_n = s_claim[2];
+    if (claim_n == 0) {
+        if (sweeping) return;
+        if (threadIdx.x == 0) s_claim[3] = atomicAdd(&qhead[nsm], 1) == (int)gridDim.x - 1 ? 1 : 0;
+        __syncthreads();
+        if (!s_claim[3]) return;
+        sweeping = true;
+        continue;
+    }
+    worked = true;
+    // wide launches rotate the warps over the entries from claim to claim so that partly filled CTAs of one SM do
+    // not pile their warps on the same sub-partitions
+    const int r_unit = S::kWide ? (warp + wpb - (claim_e / wpb) % wpb) % wpb : warp;
+    const int64_t base = r_unit < claim_n ? ((int64_t)claim_q + (int64_t)(claim_e + r_unit) * nsm) * PW : (int64_t)n_active;
     if (base >= n_active) {
         if (lockstep)
             for (int step = 0; step < c_pr.gd_max_iters; ++step) __syncthreads();
         if (lockstep_rep)
             for (int k = 0; k < PW; ++k) __syncthreads();
-        return;
-    }
-    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, PW), n, P, PW);
-    const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;
-    int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
+    } else {
     if (lane < PW) {
         const int64_t idx = base + lane;
-        const int b = idx < n_active ? act_in[idx] : -1;
+        int b = idx < n_active ? act_in[idx] : -1;
+        if (b >= 0 && sb.group_term) {
+            // `terminate` (src/ik_memetic.cpp:264-268): a species of this problem returned a value in an EARLIER
+            // generation (a flag set in this launch is not looked at: the species run in lockstep)
+            const int term = sb.group_term[problem_of(sb, b)];
+            if (term > 0 && term <= gen) {
+                finish_terminated<S>(sb, W, b, lane);
+                b = -1;
+            }
+        }
         W.pidx[lane] = b;
         W.flag[lane] = 0;
-        if (b >= 0) goal_from_pose(sb.goal_pose + 7 * (size_t)b, W.goal + 7 * lane);
+        if (b >= 0) goal_from_pose(sb.goal_pose + 7 * (size_t)problem_of(sb, b), W.goal + 7 * lane);
     }
     __syncwarp();
 
@@ -522,7 +643,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
             slot = order_ptr(sb, iter & 1, b, P)[e];
             src = pop_ptr(sb, iter & 1, b, n, P);
             dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
-            sd = sb.seed + (size_t)b * sb.seed_stride;
+            sd = sb.seed + (size_t)problem_of(sb, b) * sb.seed_stride;
             if (leader) {
                 for (int j = 0; j < n; ++j) {
                     const double v = src[(size_t)j * P + slot];
@@ -588,9 +709,11 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         double* dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
         const uint16_t* ord_in = order_ptr(sb, iter & 1, b, P);
         uint16_t* ord_out = order_ptr(sb, (iter & 1) ^ 1, b, P);
-        const double* sd = sb.seed + (size_t)b * sb.seed_stride;
+        const double* sd = sb.seed + (size_t)problem_of(sb, b) * sb.seed_stride;
         const double* g7 = W.goal + 7 * k;
         const int c0 = k * E;  // first elite column of this problem
+        const uint32_t rng_problem = (uint32_t)(sb.first_problem_index + problem_of(sb, b));
+        const uint32_t rng_species = species_of(sb, b);
         if (lane < E) {
             W.fit[lane] = W.efit[c0 + lane];
             W.pool[lane] = lane;
@@ -615,21 +738,20 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
             if (actv) {
                 const int slot = ord_in[i];
                 if (ps > 0) {
-                    const Stream st = make_stream((uint32_t)(sb.first_problem_index + b), kStreamReproduce,
-                                                  (uint32_t)iter, (uint32_t)i);
+                    const Stream st = make_stream(rng_problem, kStreamReproduce, (uint32_t)iter, (uint32_t)i, rng_species);
                     uint32_t m0, m1, m2, m3;
                     IndexWords iw;
                     iw.st = st;
-                    philox_block(st, 0, iw.h0, iw.h1, iw.h2, iw.h3);
-                    philox_block(st, 1, m0, m1, m2, m3);
+                    philox_block(sb, st, 0, iw.h0, iw.h1, iw.h2, iw.h3);
+                    philox_block(sb, st, 1, m0, m1, m2, m3);
                     iw.h4 = m2;
                     iw.h5 = m3;
                     iw.v0 = iw.v1 = iw.v2 = iw.v3 = 0;
                     iw.ovf_block = (uint32_t)(2 * n + 2);
                     iw.pos = 0;
-                    const uint32_t idxA = uniform_int_words(iw, (uint32_t)ps);
+                    const uint32_t idxA = uniform_int_words(sb, iw, (uint32_t)ps);
                     uint32_t idxB = idxA;
-                    while (idxB == idxA && ps > 1) idxB = uniform_int_words(iw, (uint32_t)ps);
+                    while (idxB == idxA && ps > 1) idxB = uniform_int_words(sb, iw, (uint32_t)ps);
                     ia = W.pool[idxA];
                     ib = W.pool[idxB];
                     const int ca = c0 + ia, cb = c0 + ib;
@@ -639,8 +761,8 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
 #pragma unroll 1
                     for (int j = 0; j < n; ++j) {
                         uint32_t a0, a1, a2, a3, u0, u1, u2, u3;
-                        philox_block(st, (uint32_t)(2 + 2 * j), a0, a1, a2, a3);
-                        philox_block(st, (uint32_t)(3 + 2 * j), u0, u1, u2, u3);
+                        philox_block(sb, st, (uint32_t)(2 + 2 * j), a0, a1, a2, a3);
+                        philox_block(sb, st, (uint32_t)(3 + 2 * j), u0, u1, u2, u3);
                         double gene = mix * W.best[j * kS + ca] + (1.0 - mix) * W.best[j * kS + cb];
                         const double rA = uniform_real_words(0.0, 1.0, a0, a1);
                         const double rB = uniform_real_words(0.0, 1.0, a2, a3);
@@ -655,12 +777,11 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                     }
                 } else {
                     // empty pool: a random individual seeded from the slot's previous occupant
-                    const Stream st = make_stream((uint32_t)(sb.first_problem_index + b), kStreamRandomChild,
-                                                  (uint32_t)iter, (uint32_t)i);
+                    const Stream st = make_stream(rng_problem, kStreamRandomChild, (uint32_t)iter, (uint32_t)i, rng_species);
                     // (only an unbounded variable reads its previous value, robot.cpp:23-30; the child slots of a fresh
                     // population are written for robots with such variables only)
                     for (int j = 0; j < n; ++j) col[j * kS] = c_rb.bounded[j] ? 0.0 : src[(size_t)j * P + slot];
-                    random_valid_configuration(st, col);
+                    random_valid_configuration(sb, st, col);
                     for (int j = 0; j < n; ++j) {
                         dst[(size_t)j * P + slot] = col[j * kS];
                         dst[(size_t)(n + j) * P + slot] = 0.0;
@@ -786,7 +907,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
             b = W.pidx[k];
             ProblemMeta m = sb.meta[b];
             const int iter = m.iter;
-            const double* sd = sb.seed + (size_t)b * sb.seed_stride;
+            const double* sd = sb.seed + (size_t)problem_of(sb, b) * sb.seed_stride;
             double* hdr = sb.hdr + (size_t)b * (n + 2);
             const double f0 = W.f0s[k];
             const bool final_gen = iter + 1 >= c_pr.max_generations;
@@ -811,6 +932,8 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                 m.status = found ? kSolved : kFailed;
                 m.iter = its;
                 write_result(sb, n, b, found, hdr, 1, sd, hdr[n], its);
+                // the first species to return a value sets `terminate` for the others (src/ik_memetic.cpp:334-346)
+                if (found && sb.group_term && sb.stop_on_first) sb.group_term[problem_of(sb, b)] = iter + 1;
                 if (sb.stats) {
                     if (found) atomicAdd(&sb.stats[2], 1ull);
                     atomicAdd(&sb.stats[3], 1ull);
@@ -843,7 +966,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         const bool again = PW == 1 && mask != 0 && gen_here + 1 < max_gens;
         if (!again) {
             int basepos = 0;
-            if (lane == 0 && mask) basepos = atomicAdd(&sb.counters[list_in ^ 1], __popc(mask));
+            if (lane == 0 && mask) basepos = atomicAdd(&sb.counters[gen + gen_here + 1], __popc(mask));
             basepos = __shfl_sync(kFull, basepos, 0);
             if (keep) act_out[basepos + __popc(mask & ((1u << lane) - 1u))] = b;
         }
@@ -858,6 +981,63 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         __syncwarp();
     }
   }
+    }  // this warp's unit
+    __syncthreads();  // s_claim is rewritten by the next claim
+  }
+}
+
+// ik_memetic's pick over the species of a problem (src/ik_memetic.cpp:334-370), one thread per problem.  The
+// reference takes the species' results in the order they are pushed: here the order of the lockstep schedule --
+// (generations executed, returned at the solution test before returned on `terminate`, species index).  With
+// stop_on_first_soln the first result, if it holds a value, is taken unconditionally; every later value replaces the
+// pick only when its fitness is strictly lower.  No value at all: NO_IK_SOLUTION, the seed, the lowest best fitness
+// and the largest generation count of the species.
+__global__ void species_pick_kernel(const __grid_constant__ SolveBuffers sb, int n, int64_t n_problems, double* solution,
+                                    int32_t* error_code, double* cost, int32_t* iterations) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_problems) return;
+    const int S = sb.n_species;
+    auto phase_of = [](int status) { return (status == kSolvedTerminated || status == kFailedTerminated) ? 1 : 0; };
+    int pick = -1;
+    double min_cost = 1.7976931348623157e308;  // std::numeric_limits<double>::max()
+    int prev_it = -1, prev_ph = -1, prev_s = -1;
+    double fail_cost = 0.0;
+    int fail_it = 0;
+    for (int k = 0; k < S; ++k) {
+        // k-th result in push order: the smallest (iterations, phase, species) above the previous one
+        int cur = -1, cit = 0, cph = 0;
+        for (int s = 0; s < S; ++s) {
+            const int64_t sp = b * S + s;
+            const int it = sb.iterations[sp], ph = phase_of(sb.meta[sp].status);
+            const bool after_prev = it > prev_it || (it == prev_it && (ph > prev_ph || (ph == prev_ph && s > prev_s)));
+            const bool before_cur = cur < 0 || it < cit || (it == cit && (ph < cph || (ph == cph && s < cur)));
+            if (after_prev && before_cur) { cur = s; cit = it; cph = ph; }
+        }
+        prev_it = cit; prev_ph = cph; prev_s = cur;
+        const int64_t sp = b * S + cur;
+        const double c = sb.cost[sp];
+        const bool has_value = sb.error_code[sp] == 1;
+        if (k == 0 || fit_less(c, fail_cost)) fail_cost = c;
+        if (cit > fail_it) fail_it = cit;
+        if (has_value && ((k == 0 && sb.stop_on_first) || c < min_cost)) {
+            pick = cur;
+            min_cost = c;
+        }
+    }
+    const double* sd = sb.seed + (size_t)b * sb.seed_stride;
+    double* out = solution + (size_t)b * n;
+    if (pick >= 0) {
+        const int64_t sp = b * S + pick;
+        for (int j = 0; j < n; ++j) out[j] = sb.solution[sp * n + j];
+        error_code[b] = 1;
+        if (cost) cost[b] = sb.cost[sp];
+        if (iterations) iterations[b] = sb.iterations[sp];
+    } else {
+        for (int j = 0; j < n; ++j) out[j] = sd[j];
+        error_code[b] = -31;
+        if (cost) cost[b] = fail_cost;
+        if (iterations) iterations[b] = fail_it;
+    }
 }
 
 // packed[b] = joints[n], cost, error_code, iterations: the row each rank contributes to the all-gather
@@ -875,6 +1055,15 @@ __global__ void pack_results_kernel(int64_t B, int n, const double* __restrict__
     else if (k == n + 1) v = (double)error_code[b];
     else v = (double)iterations[b];
     packed[idx] = v;
+}
+
+// which %smid values exist on this device (they have holes where SMs are fused off)
+__global__ void sm_discover_kernel(int* seen, int spin_cycles) {
+    if (threadIdx.x == 0) {
+        seen[sm_id() & (kSmDenseSize - 1)] = 1;
+        const long long t0 = clock64();
+        while (clock64() - t0 < spin_cycles) {}
+    }
 }
 
 __global__ void fp64_peak_kernel(double* sink, int iters) {
@@ -904,11 +1093,49 @@ MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
     s.lanes_per_elite = L;
     s.problems_per_warp = 32 / (E * L);
     s.warps = L == 1 ? kWarpsPerBlockBulk : kWarpsPerBlock;
+    // the wide flavour carves its shared memory for the largest number of problems per warp it may be given
+    const int pw_carve = L == 1 ? s.problems_per_warp : wide_problems_per_warp_max(E);
     // a large population may not leave room for 8 warps' worth of shared memory
-    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, s.problems_per_warp) > 112 * 1024) --s.warps;
+    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, pw_carve) > 112 * 1024) --s.warps;
     s.threads = 32 * s.warps;
-    s.smem = s.warps * warp_smem_bytes(n, P, s.problems_per_warp);
+    s.smem = s.warps * warp_smem_bytes(n, P, pw_carve);
     return s;
+}
+
+GenerationPlan plan_generations(int n, int P, int E, int64_t n_sub, int sm_count, long long wide_warps_per_sm,
+                                bool allow_persistent) {
+    GenerationPlan g;
+    const MemeticShape t = memetic_shape(n, P, E, 1);
+    g.threads_t = t.threads;
+    g.smem_t = t.smem;
+    // grids of resident CTAs (2 per SM for the throughput flavour, 3 for the wide one): the CTAs claim their work from
+    // the per-SM queues, in as many rounds as it takes
+    const int64_t per_block_t = (int64_t)t.problems_per_warp * t.warps;
+    int64_t blocks_t = (n_sub + per_block_t - 1) / per_block_t;
+    if (blocks_t > (int64_t)2 * sm_count) blocks_t = (int64_t)2 * sm_count;
+    g.blocks_t = (unsigned)blocks_t;
+    g.lanes_max = memetic_max_lanes_per_elite(E);
+    // largest power of two the doubling of lanes_for can reach
+    int lw = 1;
+    while (lw * 2 <= g.lanes_max) lw *= 2;
+    const MemeticShape w = memetic_shape(n, P, E, lw);
+    g.threads_w = w.threads;
+    g.smem_w = w.smem;
+    const int64_t units_w = (n_sub + w.problems_per_warp - 1) / w.problems_per_warp;
+    int64_t blocks_w = (units_w + w.warps - 1) / w.warps;
+    if (blocks_w > (int64_t)3 * sm_count) blocks_w = (int64_t)3 * sm_count;
+    g.blocks_w = (unsigned)blocks_w;
+    g.wide_units_max = (int)(blocks_w * w.warps);
+    g.wide_capacity_lanes = (long long)sm_count * wide_warps_per_sm * 32;
+    if (g.lanes_max < 2) g.wide_capacity_lanes = 0;
+    // (only once every warp has an SM sub-partition to itself: a launch per generation re-spreads the
+    // survivors over the SMs, a persistent warp stays where it started)
+    g.persistent_units_max = allow_persistent ? sm_count * 4 : 0;
+    const int l0 = lanes_for(n_sub, E, g.lanes_max, g.wide_capacity_lanes, g.wide_units_max);
+    g.use_wide = lanes_for(1, E, g.lanes_max, g.wide_capacity_lanes, g.wide_units_max) > 1;
+    g.use_throughput = l0 == 1;
+    g.first_launch_runs_all = l0 > 1 && 32 / (E * l0) == 1 && n_sub <= g.persistent_units_max;
+    return g;
 }
 
 size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 12 + 7) * kS * sizeof(double); }
@@ -1013,39 +1240,21 @@ cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int
     return cudaGetLastError();
 }
 
-cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb,
-                                      int list_in, int64_t n_active, int lanes_per_elite, int max_gens) {
-    if (n_active <= 0) return cudaSuccess;
-    MemeticShape s = memetic_shape(n, P, E, lanes_per_elite);
-    {
-        // A throughput-mode launch that does not fill the machine is bound by its most loaded SM: pick the CTA size (in warps)
-        // that minimises the warps on that SM when the CTAs are dealt round-robin (ties: the larger CTA).
-        static const int sm_count = [] {
-            int dev = 0, v = 148;
-            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-            return v > 0 ? v : 148;
-        }();
-        const int64_t n_warps = (n_active + s.problems_per_warp - 1) / s.problems_per_warp;
-        if (s.lanes_per_elite == 1 && n_warps <= (int64_t)sm_count * 16 && !std::getenv("PIK_FIXED_CTA")) {
-            int best_w = s.warps;
-            int64_t best_load = INT64_MAX;
-            for (int w = s.warps; w >= 1; --w) {
-                const int64_t ctas = (n_warps + w - 1) / w;
-                const int64_t load = ((ctas + sm_count - 1) / sm_count) * w;
-                if (load < best_load) {
-                    best_load = load;
-                    best_w = w;
-                }
-            }
-            s.warps = best_w;
-            s.threads = 32 * s.warps;
-            s.smem = s.warps * warp_smem_bytes(n, P, s.problems_per_warp);
-        }
+cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, const GenerationPlan& g, const SolveBuffers& sb,
+                                      int gen, bool wide) {
+    if (wide) {
+        PIK_DISPATCH_SPEC(spec, true, (memetic_generation_kernel<S><<<g.blocks_w, g.threads_w, g.smem_w, stream>>>(sb, gen)));
+    } else {
+        PIK_DISPATCH_SPEC(spec, false, (memetic_generation_kernel<S><<<g.blocks_t, g.threads_t, g.smem_t, stream>>>(sb, gen)));
     }
-    const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
-    const unsigned blocks = (unsigned)((n_active + per_block - 1) / per_block);
-    PIK_DISPATCH_SPEC(spec, s.lanes_per_elite > 1, (memetic_generation_kernel<S><<<blocks, s.threads, s.smem, stream>>>(
-                                sb, list_in, s.lanes_per_elite, s.problems_per_warp, max_gens)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_species_pick(cudaStream_t stream, const SolveBuffers& sb, int n, int64_t n_problems, double* solution,
+                                int32_t* error_code, double* cost, int32_t* iterations) {
+    if (n_problems <= 0) return cudaSuccess;
+    species_pick_kernel<<<(unsigned)((n_problems + 127) / 128), 128, 0, stream>>>(sb, n, n_problems, solution, error_code,
+                                                                                  cost, iterations);
     return cudaGetLastError();
 }
 
@@ -1055,6 +1264,32 @@ cudaError_t launch_pack_results(cudaStream_t stream, int64_t B, int n, const dou
     const int64_t total = B * (n + 3);
     pack_results_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(B, n, solution, cost, error_code, iterations, packed);
     return cudaGetLastError();
+}
+
+cudaError_t discover_sm_ids(cudaStream_t stream, int sm_count, unsigned short* dense) {
+    for (int i = 0; i < kSmDenseSize; ++i) dense[i] = (unsigned short)(i % sm_count);  // fallback: still correct, less even
+    int* d_seen = nullptr;
+    cudaError_t e = cudaMalloc(&d_seen, kSmDenseSize * sizeof(int));
+    if (e != cudaSuccess) return e;
+    int seen[kSmDenseSize];
+    for (int attempt = 0; attempt < 3 && e == cudaSuccess; ++attempt) {
+        e = cudaMemsetAsync(d_seen, 0, kSmDenseSize * sizeof(int), stream);
+        if (e != cudaSuccess) break;
+        sm_discover_kernel<<<sm_count * 32, 32, 0, stream>>>(d_seen, 20000 << attempt);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(seen, d_seen, sizeof(seen), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) break;
+        int count = 0;
+        for (int i = 0; i < kSmDenseSize; ++i) count += seen[i] ? 1 : 0;
+        if (count == sm_count) {
+            int next = 0;
+            for (int i = 0; i < kSmDenseSize; ++i) dense[i] = (unsigned short)(seen[i] ? next++ : 0);
+            break;
+        }
+    }
+    cudaFree(d_seen);
+    return e;
 }
 
 cudaError_t launch_fp64_peak(cudaStream_t stream, double* sink, int blocks, int threads, int iters) {

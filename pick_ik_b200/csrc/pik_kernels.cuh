@@ -39,16 +39,34 @@ int select_spec(const DevRobot& robot);
 
 cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb);
 cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb);
-// One launch advances every problem of active list `list_in` by one generation (or, with one problem per
-// warp, by up to max_gens generations) and appends the still-active ones to the other list.  n_active
-// bounds the grid.
-cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb,
-                                      int list_in, int64_t n_active, int lanes_per_elite, int max_gens);
+// The launches of a global-mode solve over n_sub sub-problems, planned once per call (nothing is read back from the
+// device while the solve runs).  Per generation: one launch of the throughput flavour (blocks_t) and one of the
+// wide flavour (blocks_w); each reads the size of the generation's active list and returns at once unless the lane
+// mapping that size calls for is its own (memetic_generation_kernel).  use_throughput / use_wide: a flavour that
+// can never run for this batch size is not enqueued; first_launch_runs_all: the batch is so small that the first
+// wide launch keeps every problem for all its generations.
+struct GenerationPlan {
+    unsigned blocks_t, blocks_w;
+    int threads_t, threads_w;
+    size_t smem_t, smem_w;
+    int lanes_max, wide_units_max, persistent_units_max;
+    long long wide_capacity_lanes;
+    bool use_throughput, use_wide, first_launch_runs_all;
+};
+GenerationPlan plan_generations(int n, int P, int E, int64_t n_sub, int sm_count, long long wide_warps_per_sm,
+                                bool allow_persistent);
+cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, const GenerationPlan& plan, const SolveBuffers& sb,
+                                      int gen, bool wide);
+// ik_memetic's pick over the species of every problem (src/ik_memetic.cpp:334-370): sb holds the per-species results
+cudaError_t launch_species_pick(cudaStream_t stream, const SolveBuffers& sb, int n, int64_t n_problems, double* solution,
+                                int32_t* error_code, double* cost, int32_t* iterations);
 // packed [B][n + 3] = joints, cost, error_code, iterations (the all-gather payload of the sharded solve)
 cudaError_t launch_pack_results(cudaStream_t stream, int64_t B, int n, const double* solution, const double* cost,
                                 const int32_t* error_code, const int32_t* iterations, double* packed);
 // FP64 FMA throughput microbenchmark (roofline denominator for the FP64 bound)
 cudaError_t launch_fp64_peak(cudaStream_t stream, double* sink, int blocks, int threads, int iters);
 cudaError_t configure_kernels();
+// dense [kSmDenseSize]: %smid -> 0 .. sm_count - 1 on the current device (synchronises `stream`)
+cudaError_t discover_sm_ids(cudaStream_t stream, int sm_count, unsigned short* dense);
 
 }  // namespace pik

@@ -8,6 +8,7 @@ namespace pik {
 constexpr int kMaxVars = 16;
 constexpr int kMaxElites = 32;       // the elites of one problem live in one warp
 constexpr int kMaxPopulation = 1024;
+constexpr int kSmDenseSize = 256;    // %smid values are below this (a power of two)
 
 enum StepKind : int { kRevX = 0, kRevY = 1, kRevZ = 2, kRevGeneral = 3, kPrismatic = 4 };
 
@@ -50,14 +51,47 @@ struct DevParams {
     int gd_max_iters;  // local: gd_max_iters; global: memetic_gd_max_iters
     int stop_on_valid, approx;
     int P, E, max_generations;
-    uint32_t seed_lo, seed_hi;
-    uint32_t round_key[20];  // Philox4x32-10 key schedule of (seed_lo, seed_hi): k0_r, k1_r for round r
     int lockstep;  // block barrier per GD step in throughput mode (PIK_NO_LOCKSTEP disables)
     int debug;  // PIK_DEBUG_PHASES: warp 0 of CTA 0 prints the cycle count of each phase of a generation
+    // Launch policy of the generation kernels, evaluated ON THE DEVICE from the size of the active list (the host
+    // enqueues every generation of a solve up front and never reads a count back):
+    int sm_count;
+    int lanes_max;               // memetic_max_lanes_per_elite(E)
+    long long wide_capacity_lanes;  // the lane mapping doubles L while n_active * E * 2L stays below this
+    int wide_units_max;          // warps a wide launch provides (grid * warps per CTA)
+    int persistent_units_max;    // a wide launch with one problem per warp and at most this many problems keeps
+                                 // every problem for all its remaining generations (0: never)
+    unsigned short sm_dense[kSmDenseSize];  // %smid -> 0 .. sm_count - 1 (%smid has holes where SMs are fused off)
 };
 
-// status codes in meta[b].status
-enum : int { kActive = 0, kSolved = 1, kFailed = 2 };
+#ifdef __CUDACC__
+#define PIK_HD __host__ __device__
+#else
+#define PIK_HD
+#endif
+
+// Lanes per elite (L) for a generation over n_active problems.  A lone warp of this code issues ~0.2 instructions
+// per cycle (dependent FP64 chains: 8-cycle DFMA latency), so an SM sub-partition needs 4-5 resident warps to stay
+// busy and a launch with fewer is latency-bound.  Throughput mode (L = 1: a whole GD instance per lane, 32 / E
+// problems per warp) executes the fewest instructions per problem but has the longest serial path per generation;
+// as the batch drains, the warp's lanes are spread over the evaluations of each GD step instead: the largest L
+// whose launch still fits the lanes the wide flavour keeps resident (capacity_lanes) and the warps its grid
+// provides (wide_units_max).  Evaluated on the device by every generation launch and on the host when a solve is
+// planned (monotone: fewer problems never give a smaller L).
+PIK_HD inline int wide_problems_per_warp_max(int E) { return 32 / (2 * E) > 1 ? 32 / (2 * E) : 1; }
+PIK_HD inline int lanes_for(long long n_active, int E, int lanes_max, long long capacity_lanes, int wide_units_max) {
+    int L = 1;
+    while (L * 2 <= lanes_max && n_active * E * (L * 2) <= capacity_lanes) {
+        const int pw = 32 / (E * L * 2);
+        if ((n_active + pw - 1) / pw > wide_units_max) break;
+        L *= 2;
+    }
+    return L;
+}
+
+// status codes in meta[b].status; kSolvedTerminated: a species that returned its best individual because another
+// species of the problem had returned a value (src/ik_memetic.cpp:264-282)
+enum : int { kActive = 0, kSolved = 1, kFailed = 2, kSolvedTerminated = 3, kFailedTerminated = 4 };
 
 // Per-problem solver state that is not an individual (MemeticIk members, ik_memetic.hpp:47-85)
 struct ProblemMeta {
@@ -67,7 +101,8 @@ struct ProblemMeta {
     int init_epoch;  // number of initPopulation calls so far (RNG stream epoch)
 };
 
-// Per-solve device buffers (all device pointers).
+// Per-solve device buffers (all device pointers).  Every per-problem solver buffer is indexed by the SUB-problem
+// sp (one per species of a problem; n_species == 1: sp == problem); goal_pose and seed by the problem sp / n_species.
 //
 // Population layout (Individual, ik_memetic.hpp:19-24, as structure-of-arrays): for problem b and
 // buffer s in {0,1}: pop[((s * B + b) * (2n+2) + row) * P + slot], rows 0..n-1 genes, n..2n-1
@@ -89,10 +124,20 @@ struct SolveBuffers {
     double* hdr;              // [B][n+2]: best genes[n], best fitness, previous fitness
     ProblemMeta* meta;        // [B]
     int32_t* active;          // [2][B] compacted lists of active problems
-    int32_t* counters;        // [2] sizes of the two lists
+    int32_t* counters;        // [max_generations + 2]: counters[g] = problems active in generation g
+    int32_t* sched;           // [max_generations + 1][sm_count + 1]: per generation launch, the heads of the per-SM
+                              // unit queues and the number of CTAs that have left (memetic_generation_kernel)
+    int32_t* group_term;      // [B / n_species] or null: generation + 1 at which a species of the problem returned a
+                              // value (the `terminate` flag of ik_memetic, src/ik_memetic.cpp:334-346), 0 = none
     unsigned long long* stats;  // [4]: problem_generations, gd_steps, solved, finished
-    int64_t B;
+    int64_t B;                // sub-problems = IK problems * n_species
     int64_t first_problem_index;
+    int32_t n_species;        // MemeticIkParams::num_threads: sub-problem sp = problem sp / n_species, species sp % n_species
+    int32_t stop_on_first;    // MemeticIkParams::stop_on_first_soln
+    // Philox4x32-10 key schedule of rng_seed: k0_r, k1_r for round r.  Per call (kernel parameter space, i.e.
+    // constant-bank operands like the tables above), so that calls that differ only in the seed share one
+    // parameter upload.
+    uint32_t round_key[20];
 };
 
 }  // namespace pik

@@ -207,3 +207,33 @@ def test_empty_batch_and_errors(solvers):
     bad = capi.default_params(memetic_elite_size=40, memetic_population_size=16)
     with pytest.raises(capi.PikError):
         solver.solve_batch(bad, np.zeros((1, 7)), np.array(robots.PANDA_HOME))
+
+
+SPECIES_CASES = [
+    ("panda", dict(memetic_population_size=16, memetic_num_threads=3, memetic_max_generations=40), 120),
+    ("panda", dict(memetic_population_size=16, memetic_num_threads=4, memetic_stop_on_first_solution=0,
+                   memetic_max_generations=25), 80),
+    ("panda", dict(memetic_population_size=16, memetic_num_threads=5, return_approximate_solution=1,
+                   memetic_max_generations=30), 80),
+    ("fetch", dict(memetic_population_size=32, memetic_num_threads=2, stop_optimization_on_valid_solution=0,
+                   memetic_max_generations=6), 60),
+    ("rr", dict(memetic_population_size=8, memetic_elite_size=2, memetic_num_threads=7, memetic_max_generations=12), 60),
+]
+
+
+@pytest.mark.parametrize("mapping", ["throughput", "wide", "default"])
+@pytest.mark.parametrize("name,kw,B", SPECIES_CASES)
+def test_memetic_species_parity(solvers, name, kw, B, mapping, monkeypatch):
+    """memetic_num_threads species per problem (src/ik_memetic.cpp:315-370): lockstep schedule, `terminate`, and the
+    min-fitness pick in arrival order, against the oracle's restatement."""
+    if mapping != "default":
+        monkeypatch.setenv("PIK_WIDE_WARPS_PER_SM", "0" if mapping == "throughput" else "1000000000")
+    chain, orobot, solver = solvers(name)
+    op, gp = both_params(mode="global", **kw)
+    goal = orc.make_targets(orobot, B)
+    seed = np.array(robots.PANDA_HOME) if name == "panda" else random_configs(orobot, B, 43)
+    first = 500
+    ref = orc.solve_batch(orobot, op, goal, seed, first_problem_index=first)
+    got = solver.solve_batch(gp, goal, seed, first_problem_index=first)
+    check_solve(got, ref, f"{name} {kw}")
+    assert 0 < (ref["error_code"] == 1).sum()
