@@ -229,6 +229,15 @@ int pik_solve_batch_sharded(pik_solver* solver, pik_comm* comm, const pik_params
                             int64_t first_problem_index, const double* goal_pose, const double* seed,
                             int64_t seed_stride, double* gathered, int32_t memory);
 
+/*
+ * Synthetic workload generator of the benchmarks: q [B][n] (host), configuration b drawn uniformly
+ * within the limits of every variable (unbounded: -pi .. pi) from the Philox4x32-10 stream (gen_seed,
+ * first_problem_index + b).  Host arithmetic only: the same bits from C, from the Python harness and from the CPU
+ * oracle (orc_random_configuration).  Targets are the FK of these configurations (pik_eval_cost's tip_pose).
+ */
+int pik_random_configurations(const pik_robot* robot, uint64_t gen_seed, int64_t first_problem_index, int64_t B,
+                              double* q);
+
 /* number of CUDA devices visible (0 if none) */
 int pik_device_count(void);
 /* page-locked host buffers for PIK_MEM_HOST calls (optional; any host memory is accepted) */

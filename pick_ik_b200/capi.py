@@ -26,7 +26,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 EXPORTS = [
     "pik_version", "pik_status_string", "pik_params_default", "pik_params_validate", "pik_robot_create",
     "pik_robot_destroy", "pik_robot_num_variables", "pik_robot_get_variable",
-    "pik_robot_is_valid_configuration", "pik_robot_chain_signature", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
+    "pik_robot_is_valid_configuration", "pik_robot_chain_signature", "pik_random_configurations", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
     "pik_solve_batch_async", "pik_solver_wait", "pik_solver_query", "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
     "pik_device_count", "pik_host_alloc", "pik_host_free", "pik_measure_fp64_peak",
     "pik_urdf_chain", "pik_comm_unique_id", "pik_comm_create", "pik_comm_destroy", "pik_comm_last_error", "pik_solve_batch_sharded",
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     L.pik_robot_is_valid_configuration.argtypes = [vp, dp]
     L.pik_robot_chain_signature.restype = C.c_char_p
     L.pik_robot_chain_signature.argtypes = [vp]
+    L.pik_random_configurations.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, dp]
     L.pik_solver_create.argtypes = [vp, C.c_int32, vp, C.POINTER(vp)]
     L.pik_solver_destroy.restype = None
     L.pik_solver_destroy.argtypes = [vp]
@@ -191,6 +192,14 @@ class Robot:
         qa = np.ascontiguousarray(q, dtype=np.float64)
         assert qa.shape == (self.n,)
         return bool(lib().pik_robot_is_valid_configuration(self.handle, qa.ctypes.data_as(C.c_void_p)))
+
+    def random_configurations(self, B: int, gen_seed: int = 0xC0FFEE, first_problem_index: int = 0) -> np.ndarray:
+        """pik_random_configurations: q [B, n] from the Philox stream (gen_seed, first_problem_index + b)."""
+        q = np.empty((B, self.n))
+        rc = lib().pik_random_configurations(self.handle, gen_seed, first_problem_index, B, q.ctypes.data)
+        if rc != PIK_OK:
+            raise PikError(rc, "pik_random_configurations")
+        return q
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None

@@ -42,7 +42,7 @@ struct pik_solver {
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     int32_t* h_counters = nullptr;            // pinned [2] (PIK_TRACE only)
-    unsigned long long* h_stats = nullptr;    // pinned [4]
+    unsigned long long* h_stats = nullptr;    // pinned [8]
     // staging for PIK_MEM_HOST calls
     DeviceArray d_goal, d_seed, d_q, d_solution, d_error, d_cost, d_iters, d_issol, d_tip, d_packed, d_gather;
     // solver state
@@ -53,6 +53,7 @@ struct pik_solver {
     // the solve in flight between pik_solve_batch_async and pik_solver_wait
     bool in_flight = false;
     bool timed_generations = false;
+    bool in_flight_species = false;
     int in_flight_status = PIK_OK;
     std::string last_error;
 };
@@ -325,6 +326,43 @@ int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q) {
     return 1;
 }
 
+// Synthetic workload generator: q*_b ~ U(min_i, max_i) per variable (unbounded: U(-pi, pi)) from the
+// Philox4x32-10 stream (key gen_seed; counter = (block i >> 1, 0, kStreamTarget << 28, b), words 2 (i & 1), +1),
+// host arithmetic only (+ - *), so a C caller, the Python harness and the CPU oracle draw the same targets.
+int pik_random_configurations(const pik_robot* robot, uint64_t gen_seed, int64_t first_problem_index, int64_t B,
+                              double* q) {
+    if (!robot || !q || B < 0 || first_problem_index < 0 || first_problem_index + B > (int64_t)0xffffffffll)
+        return PIK_E_INVALID_ARGUMENT;
+    const int n = robot->dev.n;
+    const uint32_t k0 = (uint32_t)gen_seed, k1 = (uint32_t)(gen_seed >> 32);
+    for (int64_t b = 0; b < B; ++b) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int i = 0; i < n; ++i) {
+            if ((i & 1) == 0) {
+                uint32_t c0 = (uint32_t)(i >> 1), c1 = 0, c2 = 3u << 28, c3 = (uint32_t)(first_problem_index + b);
+                uint32_t ka = k0, kb = k1;
+                for (int round = 0; round < 10; ++round) {
+                    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+                    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ ka, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ kb;
+                    c1 = (uint32_t)p1;
+                    c3 = (uint32_t)p0;
+                    c0 = n0;
+                    c2 = n2;
+                    ka += 0x9E3779B9u;
+                    kb += 0xBB67AE85u;
+                }
+                w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+            }
+            const uint32_t lo = w[2 * (i & 1)], hi = w[2 * (i & 1) + 1];
+            const double u = (double)(((((uint64_t)hi) << 32) | (uint64_t)lo) >> 11) * 0x1.0p-53;
+            const pik_variable& v = robot->vars[i];
+            const double a = v.bounded ? v.min : -M_PI, bb = v.bounded ? v.max : M_PI;
+            q[b * n + i] = a + (bb - a) * u;
+        }
+    }
+    return PIK_OK;
+}
+
 int pik_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -358,7 +396,7 @@ int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev3);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_counters), 2 * sizeof(int32_t), cudaHostAllocDefault);
     if (e == cudaSuccess)
-        e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_stats), 4 * sizeof(unsigned long long), cudaHostAllocDefault);
+        e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_stats), 8 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = configure_kernels();
     if (e == cudaSuccess) {
@@ -422,7 +460,7 @@ int finish_solve(pik_solver* s) {
     }
     s->stats.problem_generations = (int64_t)s->h_stats[0];
     s->stats.gd_steps = (int64_t)s->h_stats[1];
-    s->stats.solved = (int64_t)s->h_stats[2];
+    s->stats.solved = (int64_t)s->h_stats[s->in_flight_species ? 4 : 2];
     return PIK_OK;
 }
 
@@ -453,6 +491,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
     std::memset(&s->stats, 0, sizeof(s->stats));
     s->stats.problems = B;
     s->timed_generations = false;
+    s->in_flight_species = S > 1;
     s->in_flight_status = PIK_OK;
     if (B == 0) return PIK_OK;
     PIK_CUDA(s, cudaSetDevice(s->device));
@@ -507,12 +546,12 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
         sb.cost = r_cost;
         sb.iterations = r_iters;
     }
-    if ((rc = ensure(s, s->d_stats, 4 * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(s, s->d_stats, 8 * sizeof(unsigned long long)))) return rc;
     sb.stats = static_cast<unsigned long long*>(s->d_stats.ptr);
     GenerationPlan plan;
     std::memset(&plan, 0, sizeof(plan));
     const size_t n_counters = (size_t)pr.max_generations + 2;
-    const size_t n_sched = ((size_t)pr.max_generations + 1) * ((size_t)s->sm_count + 1);
+    const size_t n_sched = ((size_t)pr.max_generations + 1) * ((size_t)s->sm_count + 2);
     if (global) {
         const size_t F = 2 * (size_t)n + 2;
         if ((rc = ensure(s, s->d_pop, 2 * (size_t)n_sub * F * P * 8)) || (rc = ensure(s, s->d_order, 2 * (size_t)n_sub * P * 2)) ||
@@ -545,7 +584,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
             PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
             PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
         }
-        PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 4 * sizeof(unsigned long long), st));
+        PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 8 * sizeof(unsigned long long), st));
         if (!global) {
             PIK_CUDA(s, launch_gd_local(st, s->spec, n, sb));
             s->stats.kernel_launches += 1;
@@ -598,7 +637,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
             if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, r_cost, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
             if (iterations) PIK_CUDA(s, cudaMemcpyAsync(iterations, r_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
         }
-        PIK_CUDA(s, cudaMemcpyAsync(s->h_stats, sb.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        PIK_CUDA(s, cudaMemcpyAsync(s->h_stats, sb.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         PIK_CUDA(s, cudaEventRecord(s->ev1, st));
         return PIK_OK;
     };
@@ -731,7 +770,7 @@ int pik_measure_fp64_peak(pik_solver* s, double* tflops) {
     PIK_CUDA(s, cudaSetDevice(s->device));
     cudaDeviceProp prop;
     PIK_CUDA(s, cudaGetDeviceProperties(&prop, s->device));
-    int rc = ensure(s, s->d_stats, 4 * sizeof(unsigned long long));
+    int rc = ensure(s, s->d_stats, 8 * sizeof(unsigned long long));
     if (rc) return rc;
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
     double best = 0.0;

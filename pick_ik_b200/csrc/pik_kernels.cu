@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     const int units = (n_active + PW - 1) / PW;
     const int nsm = c_pr.sm_count;
     const int sigma = c_pr.sm_dense[sm_id() & (kSmDenseSize - 1)];
-    int* qhead = sb.sched + (size_t)gen * (size_t)(nsm + 1);  // [nsm] queue heads, then the count of CTAs that left
+    int* qhead = sb.sched + (size_t)gen * (size_t)(nsm + 2);  // [nsm] queue heads, CTAs that have left, units taken
     const bool persistent = S::kWide && PW == 1 && units <= c_pr.persistent_units_max && !(sb.group_term && sb.stop_on_first);
     const int max_gens = persistent ? c_pr.max_generations - gen : 1;
     // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
@@ -557,33 +557,53 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
     bool worked = false, sweeping = false;
   for (;;) {
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
         // entries of queue t: units t, t + nsm, t + 2 nsm, ...
         auto queue_len = [&](int t) { return t < units ? (units - t + nsm - 1) / nsm : 0; };
         int got_q = -1, got_e = 0, got_n = 0;
-        auto try_queue = [&](int t) {
+        auto try_queue = [&](int t) {  // one lane
             const int ql = queue_len(t);
-            if (ql > 0 && ld_volatile(&qhead[t]) < ql) {
-                const int old = atomicAdd(&qhead[t], wpb);
-                if (old < ql) {
-                    got_q = t;
-                    got_e = old;
-                    got_n = ql - old < wpb ? ql - old : wpb;
-                }
+            const int old = atomicAdd(&qhead[t], wpb);
+            if (old < ql) {
+                got_q = t;
+                got_e = old;
+                got_n = ql - old < wpb ? ql - old : wpb;
+                atomicAdd(&qhead[nsm + 1], got_n);  // units taken so far, over all queues
             }
         };
-        try_queue(sigma);
-        if (got_q < 0 && (worked || sweeping))
-            for (int d = 1; d < nsm && got_q < 0; ++d) try_queue(sigma + d < nsm ? sigma + d : sigma + d - nsm);
-        s_claim[0] = got_q;
-        s_claim[1] = got_e;
-        s_claim[2] = got_n;
+        if (lane == 0 && ld_volatile(&qhead[sigma]) < queue_len(sigma)) try_queue(sigma);
+        got_q = __shfl_sync(kFull, got_q, 0);
+        if (got_q < 0 && (worked || sweeping) && ld_volatile(&qhead[nsm + 1]) < units) {
+            // the other SMs' queues, 32 at a time, nearest first
+            for (int d0 = 1; d0 < nsm && got_q < 0; d0 += 32) {
+                const int d = d0 + lane;
+                const int t = sigma + d < nsm ? sigma + d : sigma + d - nsm;
+                const bool open = d < nsm && ld_volatile(&qhead[t]) < queue_len(t);
+                unsigned mask = __ballot_sync(kFull, open);
+                while (mask != 0 && got_q < 0) {
+                    const int l = __ffs(mask) - 1;
+                    if (lane == l) try_queue(t);
+                    got_q = __shfl_sync(kFull, got_q, l);
+                    if (got_q >= 0) {
+                        got_e = __shfl_sync(kFull, got_e, l);
+                        got_n = __shfl_sync(kFull, got_n, l);
+                    }
+                    mask &= mask - 1;
+                }
+            }
+        }
+        if (lane == 0) {
+            s_claim[0] = got_q;
+            s_claim[1] = got_e;
+            s_claim[2] = got_n;
+        }
     }
     __syncthreads();
     const int claim_q = s_claim[0], claim_e = s_claim[1], claim_n = s_claim[2];
     if (claim_n == 0) {
         if (sweeping) return;
-        if (threadIdx.x == 0) s_claim[3] = atomicAdd(&qhead[nsm], 1) == (int)gridDim.x - 1 ? 1 : 0;
+        if (threadIdx.x == 0)
+            s_claim[3] = (atomicAdd(&qhead[nsm], 1) == (int)gridDim.x - 1 && ld_volatile(&qhead[nsm + 1]) < units) ? 1 : 0;
         __syncthreads();
         if (!s_claim[3]) return;
         sweeping = true;
@@ -1030,6 +1050,7 @@ __global__ void species_pick_kernel(const __grid_constant__ SolveBuffers sb, int
         const int64_t sp = b * S + pick;
         for (int j = 0; j < n; ++j) out[j] = sb.solution[sp * n + j];
         error_code[b] = 1;
+        if (sb.stats) atomicAdd(&sb.stats[4], 1ull);  // problems with a value (stats[2] counts species)
         if (cost) cost[b] = sb.cost[sp];
         if (iterations) iterations[b] = sb.iterations[sp];
     } else {
@@ -1189,15 +1210,15 @@ int select_spec(const DevRobot& rb) {
 
 template <class S>
 static cudaError_t configure_spec(bool wide) {
-    cudaError_t e = cudaFuncSetAttribute(memetic_generation_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(memetic_generation_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess || wide) return e;
-    e = cudaFuncSetAttribute(memetic_init_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    e = cudaFuncSetAttribute(memetic_init_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gd_local_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute(gd_local_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 cudaError_t configure_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(eval_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(eval_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int spec = 0; spec < kSpecCount && e == cudaSuccess; ++spec) {
         PIK_DISPATCH_SPEC(spec, false, e = configure_spec<S>(false));
         if (e == cudaSuccess) PIK_DISPATCH_SPEC(spec, true, e = configure_spec<S>(true));

@@ -125,11 +125,11 @@ struct SolveBuffers {
     ProblemMeta* meta;        // [B]
     int32_t* active;          // [2][B] compacted lists of active problems
     int32_t* counters;        // [max_generations + 2]: counters[g] = problems active in generation g
-    int32_t* sched;           // [max_generations + 1][sm_count + 1]: per generation launch, the heads of the per-SM
-                              // unit queues and the number of CTAs that have left (memetic_generation_kernel)
+    int32_t* sched;           // [max_generations + 1][sm_count + 2]: per generation launch, the heads of the per-SM unit
+                              // queues, the number of CTAs that have left, the units taken (memetic_generation_kernel)
     int32_t* group_term;      // [B / n_species] or null: generation + 1 at which a species of the problem returned a
                               // value (the `terminate` flag of ik_memetic, src/ik_memetic.cpp:334-346), 0 = none
-    unsigned long long* stats;  // [4]: problem_generations, gd_steps, solved, finished
+    unsigned long long* stats;  // [8]: problem_generations, gd_steps, solved, finished, problems with a value (species pick)
     int64_t B;                // sub-problems = IK problems * n_species
     int64_t first_problem_index;
     int32_t n_species;        // MemeticIkParams::num_threads: sub-problem sp = problem sp / n_species, species sp % n_species
