@@ -228,6 +228,18 @@ const char* pik_comm_last_error(void);
 int pik_solve_batch_sharded(pik_solver* solver, pik_comm* comm, const pik_params* params, int64_t B_local,
                             int64_t first_problem_index, const double* goal_pose, const double* seed,
                             int64_t seed_stride, double* gathered, int32_t memory);
+/*
+ * The general form.  counts [n_ranks]: problems of every rank's shard (NULL: B_local on every rank; otherwise
+ * counts[rank] == B_local); shards may be uneven or empty (pick_ik_b200/sharding.py::shard_range).  root: the one
+ * rank that receives the block, or -1 for every rank; only receiving ranks need `gathered`
+ * ([sum counts][n + 3], rank order) and only they pay for a device-to-host copy of it (PIK_MEM_HOST).  Even
+ * shards to every rank travel as one ncclAllGather, everything else as grouped ncclSend / ncclRecv.  Every rank
+ * takes part in the exchange even if its own solve fails (its rows arrive as NaN and its call returns the
+ * error), so a failing rank does not leave the others waiting.
+ */
+int pik_solve_batch_gather(pik_solver* solver, pik_comm* comm, const pik_params* params, int64_t B_local,
+                           int64_t first_problem_index, const double* goal_pose, const double* seed,
+                           int64_t seed_stride, const int64_t* counts, int32_t root, double* gathered, int32_t memory);
 
 /*
  * Synthetic workload generator of the benchmarks: q [B][n] (host), configuration b drawn uniformly

@@ -30,6 +30,7 @@ EXPORTS = [
     "pik_solve_batch_async", "pik_solver_wait", "pik_solver_query", "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
     "pik_device_count", "pik_host_alloc", "pik_host_free", "pik_measure_fp64_peak",
     "pik_urdf_chain", "pik_comm_unique_id", "pik_comm_create", "pik_comm_destroy", "pik_comm_last_error", "pik_solve_batch_sharded",
+    "pik_solve_batch_gather",
 ]
 COMM_ID_BYTES = 128
 URDF_NAME_BYTES = 64
@@ -134,6 +135,8 @@ def lib() -> C.CDLL:
     L.pik_comm_last_error.restype = C.c_char_p
     L.pik_solve_batch_sharded.argtypes = [vp, vp, C.POINTER(Params), C.c_int64, C.c_int64, dp, dp, C.c_int64, dp,
                                           C.c_int32]
+    L.pik_solve_batch_gather.argtypes = [vp, vp, C.POINTER(Params), C.c_int64, C.c_int64, dp, dp, C.c_int64, vp,
+                                         C.c_int32, dp, C.c_int32]
     _lib = L
     return L
 
@@ -297,6 +300,21 @@ class Solver:
                                            goal_pose, seed, seed_stride, gathered, memory)
         if rc != PIK_OK:
             raise PikError(rc, "pik_solve_batch_sharded",
+                           lib().pik_solver_last_error(self.handle).decode() or lib().pik_comm_last_error().decode())
+
+    def solve_batch_gather_ptr(self, comm: "Comm", params: Params, B_local: int, first_problem_index: int,
+                               goal_pose: int, seed: int, seed_stride: int, gathered: int, memory: int = MEM_DEVICE,
+                               counts=None, root: int = -1):
+        """pik_solve_batch_gather: uneven shards (counts [n_ranks]) and / or a single receiving rank (root)."""
+        c = None
+        if counts is not None:
+            c = np.ascontiguousarray(counts, dtype=np.int64)
+            assert c.shape == (comm.n_ranks,)
+        rc = lib().pik_solve_batch_gather(self.handle, comm.handle, C.byref(params), B_local, first_problem_index,
+                                          goal_pose, seed, seed_stride, None if c is None else c.ctypes.data, root,
+                                          gathered or None, memory)
+        if rc != PIK_OK:
+            raise PikError(rc, "pik_solve_batch_gather",
                            lib().pik_solver_last_error(self.handle).decode() or lib().pik_comm_last_error().decode())
 
     def synchronize(self):

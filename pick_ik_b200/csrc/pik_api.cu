@@ -811,6 +811,12 @@ int pik_internal_pack(pik_solver* s, int64_t B, size_t packed_elems, size_t gath
     if (gather_elems && (rc = ensure(s, s->d_gather, gather_elems * sizeof(double)))) return rc;
     *packed = static_cast<double*>(s->d_packed.ptr);
     *gather = gather_elems ? static_cast<double*>(s->d_gather.ptr) : nullptr;
+    if (B < 0) {
+        // the shard failed: rows of NaN (all bits set) for the ranks that wait for them
+        PIK_CUDA(s, cudaMemsetAsync(*packed, 0xff, packed_elems * sizeof(double), s->stream));
+        return PIK_OK;
+    }
+    if (B == 0) return PIK_OK;
     PIK_CUDA(s, launch_pack_results(s->stream, B, s->robot.dev.n, static_cast<double*>(s->d_solution.ptr),
                                     static_cast<double*>(s->d_cost.ptr), static_cast<int32_t*>(s->d_error.ptr),
                                     static_cast<int32_t*>(s->d_iters.ptr), *packed));

@@ -23,6 +23,10 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -57,7 +61,9 @@ const NcclApi* nccl() {
         g_nccl.handle = h;
         g_nccl.ok = load_sym(h, "ncclGetUniqueId", g_nccl.GetUniqueId) && load_sym(h, "ncclCommInitRank", g_nccl.CommInitRank) &&
                     load_sym(h, "ncclCommDestroy", g_nccl.CommDestroy) && load_sym(h, "ncclAllGather", g_nccl.AllGather) &&
-                    load_sym(h, "ncclGetErrorString", g_nccl.GetErrorString);
+                    load_sym(h, "ncclGetErrorString", g_nccl.GetErrorString) && load_sym(h, "ncclSend", g_nccl.Send) &&
+                    load_sym(h, "ncclRecv", g_nccl.Recv) && load_sym(h, "ncclGroupStart", g_nccl.GroupStart) &&
+                    load_sym(h, "ncclGroupEnd", g_nccl.GroupEnd);
         if (!g_nccl.ok) set_error("libnccl.so.2 lacks a required symbol");
     });
     return g_nccl.ok ? &g_nccl : nullptr;
@@ -136,39 +142,91 @@ void pik_comm_destroy(pik_comm* comm) {
     delete comm;
 }
 
-int pik_solve_batch_sharded(pik_solver* solver, pik_comm* comm, const pik_params* params, int64_t B_local,
-                            int64_t first_problem_index, const double* goal_pose, const double* seed,
-                            int64_t seed_stride, double* gathered, int32_t memory) {
-    if (!solver || !comm || !gathered) return PIK_E_INVALID_ARGUMENT;
+int pik_solve_batch_gather(pik_solver* solver, pik_comm* comm, const pik_params* params, int64_t B_local,
+                           int64_t first_problem_index, const double* goal_pose, const double* seed,
+                           int64_t seed_stride, const int64_t* counts, int32_t root, double* gathered, int32_t memory) {
+    if (!solver || !comm) return PIK_E_INVALID_ARGUMENT;
     if (pik_internal_solver_device(solver) != comm->device) return PIK_E_INVALID_ARGUMENT;
+    if (root < -1 || root >= comm->n_ranks) return PIK_E_INVALID_ARGUMENT;
+    if (memory != PIK_MEM_HOST && memory != PIK_MEM_DEVICE) return PIK_E_INVALID_ARGUMENT;
+    const bool receives = root < 0 || root == comm->rank;
+    if (receives && !gathered) return PIK_E_INVALID_ARGUMENT;
+    if (B_local < 0 || (counts && counts[comm->rank] != B_local)) return PIK_E_INVALID_ARGUMENT;
     const NcclApi* api = nccl();
     if (!api) return PIK_E_NCCL;
-    int rc = pik_internal_solve_keep(solver, params, B_local, first_problem_index, goal_pose, seed, seed_stride, memory);
-    if (rc != PIK_OK || B_local == 0) return rc;
-    // the solve is enqueued; the pack and the collective go behind it on the same stream
     const int n = pik_internal_solver_num_variables(solver);
-    const size_t row = (size_t)B_local * (size_t)(n + 3);
+    const size_t w = (size_t)(n + 3);
+    bool even = true;
+    int64_t total = 0, max_count = 0;
+    for (int r = 0; r < comm->n_ranks; ++r) {
+        const int64_t c = counts ? counts[r] : B_local;
+        if (c < 0) return PIK_E_INVALID_ARGUMENT;
+        even = even && c == B_local;
+        total += c;
+        if (c > max_count) max_count = c;
+    }
+    if (total == 0) return PIK_OK;
+    // From here on this rank takes part in the exchange whatever happens to its own shard: a rank that returned
+    // early would leave the others waiting in the collective.  A failed shard travels as rows of NaN.
+    const int solve_rc =
+        B_local > 0 ? pik_internal_solve_keep(solver, params, B_local, first_problem_index, goal_pose, seed, seed_stride, memory)
+                    : PIK_OK;
     double* packed = nullptr;
     double* dst = nullptr;
     // packed shard and (for host callers) the gathered block live in the solver's staging buffers
-    rc = pik_internal_pack(solver, B_local, row, memory == PIK_MEM_HOST ? row * (size_t)comm->n_ranks : 0, &packed, &dst);
+    const size_t gather_elems = (receives && memory == PIK_MEM_HOST) ? (size_t)total * w : 0;
+    int rc = pik_internal_pack(solver, solve_rc == PIK_OK ? B_local : -B_local, (size_t)(B_local > 0 ? B_local : 1) * w,
+                               gather_elems, &packed, &dst);
     if (rc != PIK_OK) {
         pik_internal_finish(solver);
-        return rc;
+        return solve_rc != PIK_OK ? solve_rc : rc;  // no buffer to send from: the other ranks are on their own
     }
     if (memory == PIK_MEM_DEVICE) dst = gathered;
     cudaStream_t st = static_cast<cudaStream_t>(pik_internal_solver_stream(solver));
-    const ncclResult_t r = api->AllGather(packed, dst, row, ncclDouble, comm->comm, st);
+    ncclResult_t r = ncclSuccess;
+    if (root < 0 && even) {
+        r = api->AllGather(packed, dst, (size_t)B_local * w, ncclDouble, comm->comm, st);
+    } else {
+        // uneven shards, or only the root wants the block: grouped point-to-point (NCCL has no gatherv)
+        r = api->GroupStart();
+        if (receives && r == ncclSuccess) {
+            size_t off = 0;
+            for (int src = 0; src < comm->n_ranks && r == ncclSuccess; ++src) {
+                const size_t c = (size_t)(counts ? counts[src] : B_local);
+                if (c > 0) r = api->Recv(dst + off * w, c * w, ncclDouble, src, comm->comm, st);
+                off += c;
+            }
+        }
+        if (B_local > 0 && r == ncclSuccess) {
+            if (root >= 0) {
+                r = api->Send(packed, (size_t)B_local * w, ncclDouble, root, comm->comm, st);
+            } else {
+                for (int to = 0; to < comm->n_ranks && r == ncclSuccess; ++to)
+                    r = api->Send(packed, (size_t)B_local * w, ncclDouble, to, comm->comm, st);
+            }
+        }
+        const ncclResult_t re = api->GroupEnd();
+        if (r == ncclSuccess) r = re;
+    }
     if (r != ncclSuccess) {
         pik_internal_finish(solver);
-        return fail_nccl(api, r, "ncclAllGather");
+        return fail_nccl(api, r, "NCCL exchange");
     }
-    if (memory == PIK_MEM_HOST &&
-        cudaMemcpyAsync(gathered, dst, row * (size_t)comm->n_ranks * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+    if (receives && memory == PIK_MEM_HOST &&
+        cudaMemcpyAsync(gathered, dst, (size_t)total * w * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
         pik_internal_finish(solver);
         return PIK_E_CUDA;
     }
-    return pik_internal_finish(solver);
+    rc = pik_internal_finish(solver);
+    if (rc == PIK_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PIK_E_CUDA;
+    return solve_rc != PIK_OK ? solve_rc : rc;
+}
+
+int pik_solve_batch_sharded(pik_solver* solver, pik_comm* comm, const pik_params* params, int64_t B_local,
+                            int64_t first_problem_index, const double* goal_pose, const double* seed,
+                            int64_t seed_stride, double* gathered, int32_t memory) {
+    return pik_solve_batch_gather(solver, comm, params, B_local, first_problem_index, goal_pose, seed, seed_stride, nullptr,
+                                  -1, gathered, memory);
 }
 
 }  // extern "C"

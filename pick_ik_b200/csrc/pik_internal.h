@@ -13,6 +13,6 @@ void* pik_internal_solver_stream(const pik_solver* s);
 int pik_internal_finish(pik_solver* s);
 int pik_internal_solve_keep(pik_solver* s, const pik_params* params, int64_t B, int64_t first_problem_index,
                             const double* goal_pose, const double* seed, int64_t seed_stride, int32_t memory);
-// packs those results into [B][n + 3] doubles (device, solver-owned); gather_elems > 0 also reserves a
-// device block of that many doubles for the gathered result
+// packs those results into [B][n + 3] doubles (device, solver-owned; B < 0: rows of NaN for a failed shard);
+// gather_elems > 0 also reserves a device block of that many doubles for the gathered result
 int pik_internal_pack(pik_solver* s, int64_t B, size_t packed_elems, size_t gather_elems, double** packed, double** gather);

@@ -54,6 +54,52 @@ def main():
         for k in ("solution", "cost", "error_code", "iterations"):
             np.testing.assert_array_equal(got[k], whole[k], err_msg=f"rank {rank} memory {memory}: {k}")
     assert 0 < (whole["error_code"] == 1).sum()
+
+    # uneven shards (pick_ik_b200/sharding.py::shard_range on a batch that does not divide) gathered on rank 1 only
+    total_u = total - 5
+    counts = np.array([sharding.shard_range(total_u, r, world)[1] - sharding.shard_range(total_u, r, world)[0]
+                       for r in range(world)], dtype=np.int64)
+    a, b = sharding.shard_range(total_u, rank, world)
+    shard_goal = np.ascontiguousarray(goal[a:b])
+    root = world - 1
+    block = np.full((total_u, n + 3), -7.0)
+    solver.solve_batch_gather_ptr(comm, params, b - a, a, shard_goal.ctypes.data, home.ctypes.data, 0,
+                                  block.ctypes.data if rank == root else 0, capi.MEM_HOST, counts=counts, root=root)
+    if rank == root:
+        got = sharding.unpack_results(block)
+        for k in ("solution", "cost", "error_code", "iterations"):
+            np.testing.assert_array_equal(got[k], whole[k][:total_u], err_msg=f"uneven gather on root: {k}")
+    # an empty shard on rank 0, every rank receives
+    counts0 = np.array([0] + [per_rank] * (world - 1), dtype=np.int64)
+    mine = int(counts0[rank])
+    a0 = int(counts0[:rank].sum())
+    g0 = np.ascontiguousarray(goal[a0:a0 + mine]) if mine else np.zeros((1, 7))
+    block0 = np.zeros((int(counts0.sum()), n + 3))
+    solver.solve_batch_gather_ptr(comm, params, mine, a0, g0.ctypes.data, home.ctypes.data, 0, block0.ctypes.data,
+                                  capi.MEM_HOST, counts=counts0, root=-1)
+    got = sharding.unpack_results(block0)
+    for k in ("solution", "cost", "error_code", "iterations"):
+        np.testing.assert_array_equal(got[k], whole[k][:int(counts0.sum())], err_msg=f"empty shard: {k}")
+
+    # a rank whose own solve fails (invalid parameters) still takes part: its call returns the error, the others
+    # receive its rows as NaN instead of waiting forever
+    bad = capi.default_params(mode="global", memetic_population_size=32, memetic_max_generations=30)
+    if rank == 0:
+        bad.gd_step_size = -1.0
+    gathered = np.zeros((world, per_rank, n + 3))
+    a, b = sharding.shard_range(total, rank, world)
+    shard_goal = np.ascontiguousarray(goal[a:b])
+    try:
+        solver.solve_batch_sharded_ptr(comm, bad, per_rank, a, shard_goal.ctypes.data, home.ctypes.data, 0,
+                                       gathered.ctypes.data, capi.MEM_HOST)
+        failed = False
+    except capi.PikError as e:
+        failed = True
+        assert e.status == -3
+    assert failed == (rank == 0)
+    assert np.isnan(gathered[0]).all()
+    got = sharding.unpack_results(gathered[1:].reshape(-1, n + 3))
+    np.testing.assert_array_equal(got["solution"], whole["solution"][per_rank:])
     comm.close()
     solver.close()
     dist.barrier()

@@ -109,3 +109,18 @@ def test_chain_signatures():
               "rr": "identity origins", "skew6": "generic", "snake16": "generic", "single": "x-rotation origins"}  # no origin after the first joint: vacuously any pattern
     for name, sig in expect.items():
         assert capi.Robot(robots.ROBOTS[name]()).chain_signature() == sig, name
+
+
+def test_random_configurations_match_the_oracle_stream():
+    """pik_random_configurations (host) draws the bits of orc_random_configuration: the bench targets are
+    reproducible from the C side and from the oracle alike."""
+    from oracle import orc
+
+    for name in ("panda", "fetch", "ur5", "snake16"):
+        chain = robots.ROBOTS[name]()
+        robot = capi.Robot(chain)
+        orobot = orc.build_robot(chain.joint_desc())
+        q = robot.random_configurations(37, 0xC0FFEE, 1000)
+        ref = np.stack([orc.random_configuration(orobot, 0xC0FFEE, 1000 + b) for b in range(37)])
+        np.testing.assert_array_equal(q, ref)
+        assert all(robot.is_valid_configuration(row) for row in q)

@@ -108,7 +108,7 @@ def test_fetch_memetic_pop256_with_joint_costs():
     kw = dict(mode="global", memetic_population_size=256, center_joints_weight=0.01, avoid_joint_limits_weight=0.01,
               cost_threshold=0.01, position_threshold=0.01)
     params = capi.default_params(**kw)
-    B = 16384
+    B = 65536
     jd = chain.joint_desc(); mv = jd[jd["type"] != 0]
     seed = np.where(mv["bounded"] != 0, 0.5 * (mv["min_position"] + mv["max_position"]), 0.0)  # mid-range, unbounded: 0
     ident = np.zeros((B, 7)); ident[:, 3] = 1.0
@@ -118,3 +118,30 @@ def test_fetch_memetic_pop256_with_joint_costs():
     picks = np.random.default_rng(2).choice(B, 32, replace=False)
     spot_check(orc.build_robot(chain.joint_desc()), orc.default_params(**kw), goal, seed, res, 0, picks)
     solver.close()
+
+
+def test_config5_shape_131072_poses_per_gpu_sharded_with_oracle_spot_check():
+    """BASELINE.json configs[4] as written -- 131 072 Panda poses per GPU, sharded over the GPUs of the box, NCCL
+    exchange of the packed solutions -- through bench.py, which checks problems of other ranks' shards (one GPU:
+    of the batch) bit for bit against the CPU oracle and fails on any mismatch."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = min(capi.device_count(), 8)
+    n = 1 << (n.bit_length() - 1)  # 1, 2, 4 or 8
+    tail = ["--gpus", str(n), "--batch", "131072", "--steps", "1", "--warmup", "1", "--no-cpu-baseline",
+            "--no-other-configs", "--no-pipelined", "--spot-check", "48"]
+    if n == 1:
+        cmd = [sys.executable, os.path.join(root, "bench.py")] + tail
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+               "127.0.0.1", "--master-port", "29533", os.path.join(root, "bench.py")] + tail
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["n_gpus"] == n and line["config"]["poses_per_gpu"] == 131072
+    assert line["parity_spot_check"]["mismatches"] == 0 and line["parity_spot_check"]["problems_per_rank"] == 48
+    assert line["solved_frac"] > 0.98
