@@ -80,6 +80,9 @@ inline int build_dev_robot(const pik_joint_desc* joints, int n_joints, DevRobot*
         out->sign[n] = 1.0;
         if (jd.type == PIK_JOINT_PRISMATIC) {
             out->kind[n] = kPrismatic;
+            if (std::fabs(x) == 1.0 && y == 0.0 && z == 0.0) { out->kind[n] = kPrisX; out->sign[n] = x; }
+            if (x == 0.0 && std::fabs(y) == 1.0 && z == 0.0) { out->kind[n] = kPrisY; out->sign[n] = y; }
+            if (x == 0.0 && y == 0.0 && std::fabs(z) == 1.0) { out->kind[n] = kPrisZ; out->sign[n] = z; }
         } else {
             out->kind[n] = kRevGeneral;
             if (std::fabs(x) == 1.0 && y == 0.0 && z == 0.0) { out->kind[n] = kRevX; out->sign[n] = x; }

@@ -58,15 +58,22 @@ struct WarpSmem {
     int* pidx;     // [32] problem index per problem slot, or -1
     int* flag;     // [32]
     int* ctl;      // [4]
+    uint16_t* perm;  // [next power of two >= P] positions being sorted (robots with unbounded variables)
 };
 
 // fit aliases the sc rows (dead once the elite searches are done) when the population fits there
 __host__ __device__ inline bool fit_in_sc(int n, int P) { return P <= 2 * n * kS; }
 
+__host__ __device__ inline int pow2_at_least(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
 __host__ __device__ inline size_t warp_smem_bytes(int n, int P, int PW) {
     size_t d = (size_t)5 * n * kS + (fit_in_sc(n, P) ? 0 : (size_t)P) + (size_t)PW * 7 + 3 * 32;
     size_t i = 32 + 33 + 32 + 32 + 4;
-    return ((d * 8 + i * 4) + 15) & ~size_t(15);
+    return ((d * 8 + i * 4 + (size_t)pow2_at_least(P) * 2) + 15) & ~size_t(15);
 }
 
 __device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P, int PW) {
@@ -91,7 +98,8 @@ __device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P
     W.top = ip; ip += 33;
     W.pidx = ip; ip += 32;
     W.flag = ip; ip += 32;
-    W.ctl = ip;
+    W.ctl = ip; ip += 4;
+    W.perm = reinterpret_cast<uint16_t*>(ip);
     return W;
 }
 
@@ -393,7 +401,21 @@ __device__ __forceinline__ void finish_terminated(const SolveBuffers& sb, const 
 // -----------------------------------------------------------------------------------------------
 template <class S>
 __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane, bool valid, const double* g7,
-                                             const double* sd, double& best_cost_out) {
+                                             const double* sd, double& best_cost_out, long long* ph = nullptr) {
+    // ph (PIK_PHASE_TRACE builds): cycles of lane 0 in [0] sin/cos cache, [1] round A, [2] control + gradient,
+    // [3] round B, [4] accepted step
+    long long tph = 0;
+    auto mark = [&](int k) {
+#ifdef PIK_PHASE_TRACE
+        if (ph) {
+            const long long now = clock64();
+            if (k >= 0) ph[k] += now - tph;
+            tph = now;
+        }
+#else
+        (void)k; (void)tph;
+#endif
+    };
     const int n = c_rb.n;
     const int c = lane / L, gl = lane % L;
     const bool leader = gl == 0;
@@ -410,6 +432,7 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
     for (;;) {
         const bool act = __shfl_sync(kFull, act_l ? 1 : 0, c * L) != 0 && valid;
         if (!__any_sync(kFull, act)) break;
+        mark(-1);
         // sin/cos cache of the current configuration, one joint per lane
         for (int j = gl; j < n; j += L) {
             if (act) {
@@ -420,6 +443,7 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
             }
         }
         __syncwarp();
+        mark(0);
         // round A: n finite-difference pairs + the current configuration, one task per lane and sub-round
         double cur = 0.0;
         for (int k = gl; k <= n; k += L) {
@@ -435,6 +459,7 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
         }
         cur = __shfl_sync(kFull, cur, acc_lane);
         __syncwarp();
+        mark(1);
         bool improved = false;
         if (act && leader) {
             if (first) {
@@ -476,10 +501,17 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
             }
         }
         __syncwarp();
-        // round B: the line search
-        if (go && gl < 2)
+        mark(2);
+        // round B: the line search.  With at least four lanes per elite: cooperative sin/cos and a row-parallel chain
+        // walk (line_search_rows; every lane of the warp takes part); with two: one evaluation per lane.
+        if (L >= 4) {
+            const double cost = line_search_rows<S>(L, gl, go, q, g, sc, W.cs + c, g7, sd);
+            if (go && gl < 2) W.cs[gl * kS + c] = cost;
+        } else if (go && gl < 2) {
             W.cs[gl * kS + c] = eval_chain<S>(q, g, gl == 0 ? kViewMinus : kViewPlus, -1, 0.0, nullptr, nullptr, g7, sd, nullptr);
+        }
         __syncwarp();
+        mark(3);
         // the always-accepted step (ik_gradient.cpp:67-85), one joint per lane
         if (go) {
             const double p1 = W.cs[c], p3 = W.cs[kS + c];
@@ -490,6 +522,7 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
             for (int j = gl; j < n; j += L) q[j * kS] = clamp_to_limits(j, q[j * kS] - g[j * kS] * joint_diff);
         }
         __syncwarp();
+        mark(4);
     }
     best_cost_out = best_cost;
     return steps;
@@ -696,7 +729,15 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
             }
             best_cost = st.best_cost;
         } else {
+#ifdef PIK_PHASE_TRACE
+            long long ph[5] = {0, 0, 0, 0, 0};
+            const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + 7 * (valid ? k : 0), sd, best_cost, dbg ? ph : nullptr);
+            if (dbg)
+                printf("pik wide gd phases: sincos %lld  roundA %lld  control %lld  roundB %lld  accept %lld\n", ph[0], ph[1],
+                       ph[2], ph[3], ph[4]);
+#else
             const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + 7 * (valid ? k : 0), sd, best_cost);
+#endif
             if (leader) gd_steps = steps;
         }
         // genes <- best, fitness <- cost_fn(best) (== best_cost: same genes, deterministic cost),
@@ -844,14 +885,36 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         if (dbg) t_rep += clock64();
         // sortPopulation (src/ik_memetic.cpp:200-209) under the total order (fitness, position), NaN last.
         if (c_rb.any_unbounded) {
-            // whole order needed: the previous occupant of every position may seed a random individual
-            for (int i = lane; i < P; i += 32) {
-                const double fi = W.fit[i];
-                int rank = 0;
-                for (int j = 0; j < P; ++j) rank += key_less(W.fit[j], j, fi, i) ? 1 : 0;
-                ord_out[rank] = ord_in[i];
-                if (rank < E) W.top[rank] = i;
-                if (rank == P - 1) W.top[E] = i;
+            // whole order needed: the previous occupant of every position may seed a random individual.  Bitonic
+            // sort of the positions (padded to a power of two; padding sorts last) in shared memory: the key is a
+            // total order, so any sorting network gives the permutation of the reference's stable sort.
+            const int PP = pow2_at_least(P);
+            for (int i = lane; i < PP; i += 32) W.perm[i] = (uint16_t)i;
+            __syncwarp();
+            auto pos_less = [&](int a, int b) {  // positions >= P are padding
+                if (a >= P || b >= P) return a < b;
+                return key_less(W.fit[a], a, W.fit[b], b);
+            };
+            for (int k = 2; k <= PP; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = lane; t < (PP >> 1); t += 32) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // the pair (i, i + j) of this stage
+                        const int x = i | j;
+                        const int a = W.perm[i], b = W.perm[x];
+                        const bool ascending = (i & k) == 0;
+                        if (pos_less(b, a) == ascending) {
+                            W.perm[i] = (uint16_t)b;
+                            W.perm[x] = (uint16_t)a;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int r = lane; r < P; r += 32) {
+                const int i = W.perm[r];
+                ord_out[r] = ord_in[i];
+                if (r < E) W.top[r] = i;
+                if (r == P - 1) W.top[E] = i;
             }
             __syncwarp();
         } else {

@@ -10,7 +10,9 @@ constexpr int kMaxElites = 32;       // the elites of one problem live in one wa
 constexpr int kMaxPopulation = 1024;
 constexpr int kSmDenseSize = 256;    // %smid values are below this (a power of two)
 
-enum StepKind : int { kRevX = 0, kRevY = 1, kRevZ = 2, kRevGeneral = 3, kPrismatic = 4 };
+// kPrisX/Y/Z: prismatic along +-x / y / z (sign in DevRobot::sign): t += column * (sign * q), which is what the general
+// form computes up to the sign of exact zeros (fma(x, +-0, t) == t)
+enum StepKind : int { kRevX = 0, kRevY = 1, kRevZ = 2, kRevGeneral = 3, kPrismatic = 4, kPrisX = 5, kPrisY = 6, kPrisZ = 7 };
 
 // Sparsity pattern of a constant rotation (URDF origins are mostly rotations about one coordinate axis, often
 // by multiples of pi/2): entries that are exactly 0 or 1 need no arithmetic -- x * 1 == x and fma(x, 0, y) == y
