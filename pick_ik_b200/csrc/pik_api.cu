@@ -586,7 +586,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
         }
         PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 8 * sizeof(unsigned long long), st));
         if (!global) {
-            PIK_CUDA(s, launch_gd_local(st, s->spec, n, sb));
+            PIK_CUDA(s, launch_gd_local(st, s->spec, n, sb, s->sm_count));
             s->stats.kernel_launches += 1;
         } else {
             PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, n_counters * sizeof(int32_t), st));

@@ -171,59 +171,106 @@ __global__ void __launch_bounds__(kThreads) eval_cost_kernel(int64_t B, const do
 // -----------------------------------------------------------------------------------------------
 // ik_gradient (src/ik_gradient.cpp:96-139), one problem per lane, whole loop on chip
 // -----------------------------------------------------------------------------------------------
+// Problems converge after very different numbers of iterations (a few ... gd_max_iters), so a lane that has finished
+// its problem takes the next one from a device-wide counter instead of idling until the slowest lane of its warp is
+// done: the warp keeps all its lanes in the same step() code whatever problem each of them is on.
 template <class S>
 __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constant__ SolveBuffers sb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (5 * n + 12 + 7) * kS;
-    const int64_t b = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (b >= sb.B) return;
     GdState st{base + lane, base + (size_t)n * kS + lane, base + (size_t)2 * n * kS + lane,
                base + (size_t)3 * n * kS + lane, base + (size_t)5 * n * kS + lane, 0.0, 0.0};
     double* g7 = base + (size_t)(5 * n + 12) * kS + lane * 7;  // 7 contiguous doubles per lane
-    const double* sd = sb.seed + b * sb.seed_stride;
-    for (int j = 0; j < n; ++j) {
-        st.q[j * kS] = sd[j];
-        st.best[j * kS] = sd[j];
-        st.g[j * kS] = 0.0;
-    }
-    goal_from_pose(sb.goal_pose + 7 * b, g7);
-    double aux[5];
-    const double c0 = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, aux);
-    bool found = false;
+    unsigned long long* next_problem = reinterpret_cast<unsigned long long*>(sb.stats + 5);
+    int64_t b = -1;
+    const double* sd = nullptr;
+    bool running = false;   // this lane is inside the iteration loop of problem b
+    bool drained = false;   // the counter has run past the batch
     int iters = 0;
-    unsigned long long steps = 0;
-    double out_cost = c0;
-    if (c_pr.stop_on_valid && solution_from_aux(aux)) {  // ik_gradient.cpp:102-104
-        found = true;
-    } else {
-        st.local_cost = st.best_cost = c0;  // GradientIk::from
-        double previous_cost = 0.0;
-        while (iters < c_pr.gd_max_iters) {
-            const bool improved = gd_step<S, true>(st, g7, sd, aux);
-            ++steps;
-            // best == local when improved, so aux describes best (ik_gradient.cpp:117-121)
-            if (improved && c_pr.stop_on_valid && solution_from_aux(aux)) {
-                found = true;
-                break;
+    double previous_cost = 0.0;
+    unsigned long long steps = 0, solved = 0, finished = 0;
+    double aux[5];
+    for (;;) {
+        // lanes without a problem take the next ones (one atomic per warp)
+        const unsigned want = __ballot_sync(kFull, !running && !drained);
+        if (want) {
+            unsigned long long first = 0;
+            if (lane == __ffs(want) - 1) first = atomicAdd(next_problem, (unsigned long long)__popc(want));
+            first = __shfl_sync(kFull, first, __ffs(want) - 1);
+            if (!running && !drained) {
+                b = (int64_t)first + __popc(want & ((1u << lane) - 1u));
+                if (b >= sb.B) {
+                    drained = true;
+                } else {
+                    sd = sb.seed + b * sb.seed_stride;
+                    for (int j = 0; j < n; ++j) {
+                        st.q[j * kS] = sd[j];
+                        st.best[j * kS] = sd[j];
+                        st.g[j * kS] = 0.0;
+                    }
+                    goal_from_pose(sb.goal_pose + 7 * b, g7);
+                    const double c0 = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, aux);
+                    if (c_pr.stop_on_valid && solution_from_aux(aux)) {  // ik_gradient.cpp:102-104
+                        write_result(sb, n, b, true, st.best, kS, sd, c0, 0);
+                        ++solved;
+                        ++finished;
+                    } else {
+                        st.local_cost = st.best_cost = c0;  // GradientIk::from
+                        previous_cost = 0.0;
+                        iters = 0;
+                        running = true;
+                    }
+                }
             }
-            if (fabs(st.local_cost - previous_cost) <= c_pr.min_cost_delta) break;  // ik_gradient.cpp:123-125
-            previous_cost = st.local_cost;
-            ++iters;
         }
-        if (!found && !c_pr.stop_on_valid) {  // ik_gradient.cpp:130-132
-            eval_chain<S>(st.best, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
-            found = solution_from_aux(aux);
+        if (!__any_sync(kFull, running)) {
+            if (__all_sync(kFull, drained)) break;
+            continue;
         }
-        if (!found && c_pr.approx) found = true;  // ik_gradient.cpp:134-136
-        out_cost = st.best_cost;
+        if (running) {
+            bool found = false, stop = iters >= c_pr.gd_max_iters;
+            if (!stop) {
+                const bool improved = gd_step<S, true>(st, g7, sd, aux);
+                ++steps;
+                // best == local when improved, so aux describes best (ik_gradient.cpp:117-121)
+                if (improved && c_pr.stop_on_valid && solution_from_aux(aux)) {
+                    found = true;
+                    stop = true;
+                } else if (fabs(st.local_cost - previous_cost) <= c_pr.min_cost_delta) {  // ik_gradient.cpp:123-125
+                    stop = true;
+                } else {
+                    previous_cost = st.local_cost;
+                    ++iters;
+                    stop = iters >= c_pr.gd_max_iters;
+                }
+            }
+            if (stop) {
+                if (!found && !c_pr.stop_on_valid) {  // ik_gradient.cpp:130-132
+                    eval_chain<S>(st.best, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, g7, sd, aux);
+                    found = solution_from_aux(aux);
+                }
+                if (!found && c_pr.approx) found = true;  // ik_gradient.cpp:134-136
+                write_result(sb, n, b, found, st.best, kS, sd, st.best_cost, iters);
+                if (found) ++solved;
+                ++finished;
+                running = false;
+            }
+        }
     }
-    write_result(sb, n, b, found, st.best, kS, sd, out_cost, iters);
     if (sb.stats) {
-        atomicAdd(&sb.stats[1], steps);
-        if (found) atomicAdd(&sb.stats[2], 1ull);
-        atomicAdd(&sb.stats[3], 1ull);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            steps += __shfl_xor_sync(kFull, steps, o);
+            solved += __shfl_xor_sync(kFull, solved, o);
+            finished += __shfl_xor_sync(kFull, finished, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&sb.stats[1], steps);
+            atomicAdd(&sb.stats[2], solved);
+            atomicAdd(&sb.stats[3], finished);
+        }
     }
 }
 
@@ -1305,9 +1352,12 @@ cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double
     return cudaGetLastError();
 }
 
-cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb) {
+cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb, int sm_count) {
     if (sb.B <= 0) return cudaSuccess;
-    const unsigned blocks = (unsigned)((sb.B + kThreads - 1) / kThreads);
+    // resident CTAs only (3 per SM at 168 registers): the lanes pull their problems from a counter
+    int64_t blocks64 = (sb.B + kThreads - 1) / kThreads;
+    if (blocks64 > (int64_t)3 * sm_count) blocks64 = (int64_t)3 * sm_count;
+    const unsigned blocks = (unsigned)blocks64;
     PIK_DISPATCH_SPEC(spec, false, (gd_local_kernel<S><<<blocks, kThreads, gd_local_smem_bytes(n), stream>>>(sb)));
     return cudaGetLastError();
 }

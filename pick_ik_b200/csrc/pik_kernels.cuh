@@ -37,7 +37,7 @@ cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double
 enum : int { kSpecGeneric = 0, kSpecAllZ7 = 1, kSpecOrgIdentity = 2, kSpecOrgRotX = 3, kSpecOrgRotY = 4, kSpecCount = 5 };
 int select_spec(const DevRobot& robot);
 
-cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb);
+cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb, int sm_count);
 cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb);
 // The launches of a global-mode solve over n_sub sub-problems, planned once per call (nothing is read back from the
 // device while the solve runs).  Per generation: one launch of the throughput flavour (blocks_t) and one of the
