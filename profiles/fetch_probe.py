@@ -15,6 +15,8 @@ solver = capi.Solver(robot)
 if name == "fetch":
     kw = dict(mode="global", memetic_population_size=256, center_joints_weight=0.01, avoid_joint_limits_weight=0.01,
               cost_threshold=0.01, position_threshold=0.01)
+    if os.environ.get("PROBE_NO_GOALS"):
+        kw.update(center_joints_weight=0.0, avoid_joint_limits_weight=0.0)
     seed = np.array([robot.variable(i).mid if robot.variable(i).bounded else 0.0 for i in range(robot.n)])
 elif name == "ur5":
     kw = dict(mode="local")
