@@ -1297,6 +1297,9 @@ int select_spec(const DevRobot& rb) {
     if (rb.n == 7 && kinds == kKindsAllZ7 && rb.has_tip && unit_sign && !std::getenv("PIK_NO_STATIC") &&
         origins_have_pattern(rb, SpecAllZ7T::origin_cls, SpecAllZ7T::tip_cls))
         return kSpecAllZ7;
+    // the origin-pattern kernels carry no general-axis joint path
+    for (int j = 0; j < rb.n; ++j)
+        if (rb.kind[j] == kRevGeneral || rb.kind[j] == kPrismatic) return kSpecGeneric;
     if (origins_have_pattern(rb, kOrgIdentity, kOrgIdentity)) return kSpecOrgIdentity;
     if (origins_have_pattern(rb, kOrgRotX, kOrgGeneral)) return kSpecOrgRotX;
     if (origins_have_pattern(rb, kOrgRotY, kOrgGeneral)) return kSpecOrgRotY;
