@@ -54,6 +54,10 @@ struct pik_solver {
     bool in_flight = false;
     bool timed_generations = false;
     bool in_flight_species = false;
+    int in_flight_slices = 1;
+    // sub-batches of a large global-mode solve: streams of descending priority and their completion events
+    std::vector<cudaStream_t> sub_streams;
+    std::vector<cudaEvent_t> sub_done;
     int in_flight_status = PIK_OK;
     std::string last_error;
 };
@@ -112,6 +116,7 @@ struct DeviceConstants {
     cudaEvent_t uploaded = nullptr;     // recorded behind the last upload
 };
 constexpr int kMaxDevices = 64;
+constexpr int kMaxSubBatches = 8;
 DeviceConstants g_constants[kMaxDevices];
 
 // Makes (rb, pr) the constants of s->device for the work s is about to enqueue on its stream.
@@ -396,7 +401,7 @@ int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev3);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_counters), 2 * sizeof(int32_t), cudaHostAllocDefault);
     if (e == cudaSuccess)
-        e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_stats), 8 * sizeof(unsigned long long), cudaHostAllocDefault);
+        e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_stats), kMaxSubBatches * 8 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = configure_kernels();
     if (e == cudaSuccess) {
@@ -425,6 +430,11 @@ void pik_solver_destroy(pik_solver* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->ev1) constants_forget(s, s->ev1);
+    for (cudaStream_t st : s->sub_streams) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+    }
+    for (cudaEvent_t ev : s->sub_done) cudaEventDestroy(ev);
     DeviceArray* arrays[] = {&s->d_goal, &s->d_seed, &s->d_q, &s->d_solution, &s->d_error, &s->d_cost, &s->d_iters,
                              &s->d_issol, &s->d_tip, &s->d_packed, &s->d_gather, &s->d_pop, &s->d_order, &s->d_hdr, &s->d_meta, &s->d_active,
                              &s->d_counters, &s->d_sched, &s->d_stats, &s->d_sub_solution, &s->d_sub_error, &s->d_sub_cost, &s->d_sub_iters,
@@ -458,9 +468,56 @@ int finish_solve(pik_solver* s) {
         PIK_CUDA(s, cudaEventElapsedTime(&ms, s->ev2, s->ev3));
         s->stats.generation_ms = ms;
     }
-    s->stats.problem_generations = (int64_t)s->h_stats[0];
-    s->stats.gd_steps = (int64_t)s->h_stats[1];
-    s->stats.solved = (int64_t)s->h_stats[s->in_flight_species ? 4 : 2];
+    s->stats.problem_generations = s->stats.gd_steps = s->stats.solved = 0;
+    for (int k = 0; k < s->in_flight_slices; ++k) {
+        s->stats.problem_generations += (int64_t)s->h_stats[8 * k + 0];
+        s->stats.gd_steps += (int64_t)s->h_stats[8 * k + 1];
+        s->stats.solved += (int64_t)s->h_stats[8 * k + 2];
+    }
+    // (the pick over species counts the problems with a value in slot 4 of the first block)
+    if (s->in_flight_species) s->stats.solved = (int64_t)s->h_stats[4];
+    return PIK_OK;
+}
+
+// Sub-batches of a global-mode solve (EXPERIMENT, off by default: PIK_SUB_BATCHES=K).  A batch spends most of its time
+// in generations whose active list no longer fills the device, so the batch can be cut into K contiguous sub-batches,
+// each a complete solve of its own (own active lists, counters and launches; RNG streams keyed by the global
+// problem index, so the results are those of the undivided batch bit for bit) on its own stream of descending
+// priority, in the hope that the throughput-bound head of one sub-batch runs in the shadow of the under-filled
+// generations of another.  Measured on B200 (profiles/r02_notes.md): it does not pay -- 68.3 ms undivided, 76.2 ms
+// for K = 2, 100.6 ms for K = 4 per 65 536 Panda poses.  CTAs are not preempted: the latency-critical launches of the
+// sub-batch that is ahead queue behind the resident (persistent) CTAs of the others, and every launch, including
+// the ones that find nothing to do, needs SM slots to run its grid.  Two whole batches in flight on two solvers
+// (pik_solve_batch_async), whose phases drift apart by themselves, do gain (bench.py "pipelined").
+int sub_batch_count(int64_t n_sub, bool trace) {
+    (void)n_sub;
+    if (trace) return 1;
+    if (const char* env = std::getenv("PIK_SUB_BATCHES")) {
+        const long v = std::atol(env);
+        if (v >= 1) return (int)(v > kMaxSubBatches ? kMaxSubBatches : v);
+    }
+    return 1;
+}
+
+int ensure_sub_streams(pik_solver* s, int K) {
+    if ((int)s->sub_streams.size() >= K) return PIK_OK;
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    PIK_CUDA(s, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    while ((int)s->sub_streams.size() < K) {
+        const int k = (int)s->sub_streams.size();
+        int prio = hi + k;
+        if (prio > lo) prio = lo;
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        PIK_CUDA(s, cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio));
+        const cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            cudaStreamDestroy(st);
+            return fail_cuda(s, e, "cudaEventCreateWithFlags");
+        }
+        s->sub_streams.push_back(st);
+        s->sub_done.push_back(ev);
+    }
     return PIK_OK;
 }
 
@@ -492,13 +549,19 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
     s->stats.problems = B;
     s->timed_generations = false;
     s->in_flight_species = S > 1;
+    s->in_flight_slices = 1;
     s->in_flight_status = PIK_OK;
     if (B == 0) return PIK_OK;
     PIK_CUDA(s, cudaSetDevice(s->device));
     DevParams pr = make_dev_params(*params);
     const int P = pr.P;
     const size_t seed_elems = seed_stride ? (size_t)B * n : (size_t)n;
+    const bool trace = trace_enabled();
+    const int K = global ? sub_batch_count(n_sub, trace) : 1;
+    if (K > 1 && (rc = ensure_sub_streams(s, K)) != PIK_OK) return rc;
+    s->in_flight_slices = K;
 
+    // the whole batch as the kernels address it; the sub-batches below are windows into these arrays
     SolveBuffers sb;
     std::memset(&sb, 0, sizeof(sb));
     sb.B = n_sub;
@@ -546,27 +609,29 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
         sb.cost = r_cost;
         sb.iterations = r_iters;
     }
-    if ((rc = ensure(s, s->d_stats, 8 * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(s, s->d_stats, (size_t)K * 8 * sizeof(unsigned long long)))) return rc;
     sb.stats = static_cast<unsigned long long*>(s->d_stats.ptr);
     GenerationPlan plan;
     std::memset(&plan, 0, sizeof(plan));
     const size_t n_counters = (size_t)pr.max_generations + 2;
     const size_t n_sched = ((size_t)pr.max_generations + 1) * ((size_t)s->sm_count + 2);
+    const int64_t slice_problems = (B + K - 1) / K;  // problems per sub-batch (the last one may be shorter)
     if (global) {
         const size_t F = 2 * (size_t)n + 2;
         if ((rc = ensure(s, s->d_pop, 2 * (size_t)n_sub * F * P * 8)) || (rc = ensure(s, s->d_order, 2 * (size_t)n_sub * P * 2)) ||
             (rc = ensure(s, s->d_hdr, (size_t)n_sub * (n + 2) * 8)) || (rc = ensure(s, s->d_meta, (size_t)n_sub * sizeof(ProblemMeta))) ||
-            (rc = ensure(s, s->d_active, 2 * (size_t)n_sub * 4)) || (rc = ensure(s, s->d_counters, n_counters * 4)) ||
-            (rc = ensure(s, s->d_sched, n_sched * 4)))
+            (rc = ensure(s, s->d_active, 2 * (size_t)n_sub * 4)) || (rc = ensure(s, s->d_counters, (size_t)K * n_counters * 4)) ||
+            (rc = ensure(s, s->d_sched, (size_t)K * n_sched * 4)))
             return rc;
-        sb.sched = static_cast<int32_t*>(s->d_sched.ptr);
         sb.pop = static_cast<double*>(s->d_pop.ptr);
         sb.order = static_cast<uint16_t*>(s->d_order.ptr);
         sb.hdr = static_cast<double*>(s->d_hdr.ptr);
         sb.meta = static_cast<ProblemMeta*>(s->d_meta.ptr);
         sb.active = static_cast<int32_t*>(s->d_active.ptr);
         sb.counters = static_cast<int32_t*>(s->d_counters.ptr);
-        plan = plan_generations(n, P, pr.E, n_sub, s->sm_count, wide_warps_per_sm(), !trace_each_generation());
+        sb.sched = static_cast<int32_t*>(s->d_sched.ptr);
+        // one plan, sized for the largest sub-batch, serves every sub-batch
+        plan = plan_generations(n, P, pr.E, slice_problems * S, s->sm_count, wide_warps_per_sm(), !trace_each_generation());
         pr.sm_count = s->sm_count;
         pr.lanes_max = plan.lanes_max;
         pr.wide_capacity_lanes = plan.wide_capacity_lanes;
@@ -574,6 +639,36 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
         pr.persistent_units_max = plan.persistent_units_max;
         std::memcpy(pr.sm_dense, s->sm_dense, sizeof(pr.sm_dense));
     }
+
+    // window k of the batch: problems [p0, p0 + pk), sub-problems [p0 S, (p0 + pk) S)
+    auto slice = [&](int k) {
+        SolveBuffers w = sb;
+        const int64_t p0 = (int64_t)k * slice_problems;
+        const int64_t pk = (p0 + slice_problems <= B ? slice_problems : B - p0);
+        const int64_t s0 = p0 * S;
+        const size_t F = 2 * (size_t)n + 2;
+        w.B = pk * S;
+        w.first_problem_index = first_problem_index + p0;
+        w.goal_pose = sb.goal_pose + 7 * (size_t)p0;
+        w.seed = sb.seed + (size_t)seed_stride * (size_t)p0;
+        w.solution = sb.solution + (size_t)s0 * n;
+        w.error_code = sb.error_code + s0;
+        w.cost = sb.cost ? sb.cost + s0 : nullptr;
+        w.iterations = sb.iterations ? sb.iterations + s0 : nullptr;
+        if (global) {
+            w.pop = sb.pop + 2 * (size_t)s0 * F * P;   // [2][w.B][F][P] of its own
+            w.order = sb.order + 2 * (size_t)s0 * P;  // [2][w.B][P]
+            w.hdr = sb.hdr + (size_t)s0 * (n + 2);
+            w.meta = sb.meta + s0;
+            w.active = sb.active + 2 * (size_t)s0;     // [2][w.B]
+            w.counters = sb.counters + (size_t)k * n_counters;
+            w.sched = sb.sched + (size_t)k * n_sched;
+            if (sb.group_term) w.group_term = sb.group_term + p0;
+        }
+        w.stats = sb.stats + (size_t)k * 8;
+        w.sm_rotation = K > 1 ? (int32_t)(((int64_t)k * s->sm_count) / K) : 0;
+        return w;
+    };
 
     cudaStream_t st = s->stream;
     if ((rc = constants_acquire(s, s->robot.dev, pr)) != PIK_OK) return rc;
@@ -584,42 +679,55 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
             PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
             PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
         }
-        PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, 8 * sizeof(unsigned long long), st));
+        PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, (size_t)K * 8 * sizeof(unsigned long long), st));
         if (!global) {
             PIK_CUDA(s, launch_gd_local(st, s->spec, n, sb, s->sm_count));
             s->stats.kernel_launches += 1;
         } else {
-            PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, n_counters * sizeof(int32_t), st));
-            PIK_CUDA(s, cudaMemsetAsync(sb.sched, 0, n_sched * sizeof(int32_t), st));
+            PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, (size_t)K * n_counters * sizeof(int32_t), st));
+            PIK_CUDA(s, cudaMemsetAsync(sb.sched, 0, (size_t)K * n_sched * sizeof(int32_t), st));
             if (sb.group_term) PIK_CUDA(s, cudaMemsetAsync(sb.group_term, 0, (size_t)B * sizeof(int32_t), st));
-            PIK_CUDA(s, launch_memetic_init(st, s->spec, n, P, pr.E, sb));
-            s->stats.kernel_launches += 1;
             PIK_CUDA(s, cudaEventRecord(s->ev2, st));
-            const bool trace = trace_enabled();
-            const int n_gens = plan.first_launch_runs_all ? 1 : pr.max_generations;
-            for (int gen = 0; gen < n_gens; ++gen) {
-                if (trace) PIK_CUDA(s, cudaEventRecord(s->ev2, st));
-                if (plan.use_throughput) {
-                    PIK_CUDA(s, launch_memetic_generation(st, s->spec, plan, sb, gen, false));
-                    s->stats.kernel_launches += 1;
+            for (int k = 0; k < K; ++k) {
+                const SolveBuffers w = slice(k);
+                if (w.B <= 0) continue;
+                cudaStream_t sk = st;
+                if (K > 1) {
+                    sk = s->sub_streams[k];
+                    PIK_CUDA(s, cudaStreamWaitEvent(sk, s->ev2, 0));  // inputs and cleared counters are in place
                 }
-                if (plan.use_wide) {
-                    PIK_CUDA(s, launch_memetic_generation(st, s->spec, plan, sb, gen, true));
-                    s->stats.kernel_launches += 1;
+                PIK_CUDA(s, launch_memetic_init(sk, s->spec, n, P, pr.E, w));
+                s->stats.kernel_launches += 1;
+                if (K == 1) PIK_CUDA(s, cudaEventRecord(s->ev2, st));
+                const int n_gens = plan.first_launch_runs_all ? 1 : pr.max_generations;
+                for (int gen = 0; gen < n_gens; ++gen) {
+                    if (trace) PIK_CUDA(s, cudaEventRecord(s->ev2, st));
+                    if (plan.use_throughput) {
+                        PIK_CUDA(s, launch_memetic_generation(sk, s->spec, plan, w, gen, false));
+                        s->stats.kernel_launches += 1;
+                    }
+                    if (plan.use_wide) {
+                        PIK_CUDA(s, launch_memetic_generation(sk, s->spec, plan, w, gen, true));
+                        s->stats.kernel_launches += 1;
+                    }
+                    if (k == 0) s->stats.generation_launches += 1;
+                    if (trace) {
+                        // PIK_TRACE: host-synchronous, one line per generation (experiments only; one sub-batch)
+                        PIK_CUDA(s, cudaEventRecord(s->ev3, st));
+                        PIK_CUDA(s, cudaMemcpyAsync(s->h_counters, w.counters + gen, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                        PIK_CUDA(s, cudaStreamSynchronize(st));
+                        float gms = 0.f;
+                        PIK_CUDA(s, cudaEventElapsedTime(&gms, s->ev2, s->ev3));
+                        s->stats.generation_ms += gms;
+                        const int n_active = s->h_counters[0];
+                        std::fprintf(stderr, "pik gen %3d active %8d lanes %2d  %8.3f ms\n", gen, n_active,
+                                     lanes_for(n_active, pr.E, pr.lanes_max, pr.wide_capacity_lanes, pr.wide_units_max), gms);
+                        if (s->h_counters[1] == 0) break;
+                    }
                 }
-                s->stats.generation_launches += 1;
-                if (trace) {
-                    // PIK_TRACE: host-synchronous, one line per generation (experiments only)
-                    PIK_CUDA(s, cudaEventRecord(s->ev3, st));
-                    PIK_CUDA(s, cudaMemcpyAsync(s->h_counters, sb.counters + gen, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-                    PIK_CUDA(s, cudaStreamSynchronize(st));
-                    float gms = 0.f;
-                    PIK_CUDA(s, cudaEventElapsedTime(&gms, s->ev2, s->ev3));
-                    s->stats.generation_ms += gms;
-                    const int n_active = s->h_counters[0];
-                    std::fprintf(stderr, "pik gen %3d active %8d lanes %2d  %8.3f ms\n", gen, n_active,
-                                 lanes_for(n_active, pr.E, pr.lanes_max, pr.wide_capacity_lanes, pr.wide_units_max), gms);
-                    if (s->h_counters[1] == 0) break;
+                if (K > 1) {
+                    PIK_CUDA(s, cudaEventRecord(s->sub_done[k], sk));
+                    PIK_CUDA(s, cudaStreamWaitEvent(st, s->sub_done[k], 0));
                 }
             }
             if (!trace) {
@@ -637,14 +745,15 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
             if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, r_cost, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
             if (iterations) PIK_CUDA(s, cudaMemcpyAsync(iterations, r_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
         }
-        PIK_CUDA(s, cudaMemcpyAsync(s->h_stats, sb.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        PIK_CUDA(s, cudaMemcpyAsync(s->h_stats, sb.stats, (size_t)K * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         PIK_CUDA(s, cudaEventRecord(s->ev1, st));
         return PIK_OK;
     };
     rc = issue();
     if (rc != PIK_OK) {
-        // kernels already issued may still read the constants: drain the stream before anyone replaces them
+        // kernels already issued may still read the constants: drain the streams before anyone replaces them
         cudaStreamSynchronize(st);
+        for (int k = 0; k < K && K > 1; ++k) cudaStreamSynchronize(s->sub_streams[k]);
         constants_commit(s, nullptr);
         return rc;
     }

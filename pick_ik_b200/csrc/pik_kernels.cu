@@ -625,6 +625,14 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     const int nsm = c_pr.sm_count;
     const int sigma = c_pr.sm_dense[sm_id() & (kSmDenseSize - 1)];
     int* qhead = sb.sched + (size_t)gen * (size_t)(nsm + 2);  // [nsm] queue heads, CTAs that have left, units taken
+    // Units are dealt to the queues in chunks: one unit at a time for the throughput flavour (every SM the same number
+    // of warps, +-1), a CTA's worth for the wide flavour (a launch bound by one warp's latency loses nothing when its
+    // warps share an SM, and the fewer CTAs it keeps resident the more room there is for the launches of the other
+    // sub-batches of the solve, which run beside it).  Dealing starts at queue sm_rotation, so that the sub-batches
+    // of a solve do not all begin on the same SMs.
+    const int chunk = S::kWide ? wpb : 1;
+    const int n_chunks = (units + chunk - 1) / chunk;
+    const int rot = sb.sm_rotation % nsm;
     const bool persistent = S::kWide && PW == 1 && units <= c_pr.persistent_units_max && !(sb.group_term && sb.stop_on_first);
     const int max_gens = persistent ? c_pr.max_generations - gen : 1;
     // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
@@ -639,7 +647,10 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
   for (;;) {
     if (warp == 0) {
         // entries of queue t: units t, t + nsm, t + 2 nsm, ...
-        auto queue_len = [&](int t) { return t < units ? (units - t + nsm - 1) / nsm : 0; };
+        auto queue_len = [&](int t) {
+            const int tq = t - rot >= 0 ? t - rot : t - rot + nsm;  // the queue's rank in dealing order
+            return tq < n_chunks ? ((n_chunks - tq + nsm - 1) / nsm) * chunk : 0;
+        };
         int got_q = -1, got_e = 0, got_n = 0;
         auto try_queue = [&](int t) {  // one lane
             const int ql = queue_len(t);
@@ -653,7 +664,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         };
         if (lane == 0 && ld_volatile(&qhead[sigma]) < queue_len(sigma)) try_queue(sigma);
         got_q = __shfl_sync(kFull, got_q, 0);
-        if (got_q < 0 && (worked || sweeping) && ld_volatile(&qhead[nsm + 1]) < units) {
+        if (got_q < 0 && (worked || sweeping) && ld_volatile(&qhead[nsm + 1]) < n_chunks * chunk) {
             // the other SMs' queues, 32 at a time, nearest first
             for (int d0 = 1; d0 < nsm && got_q < 0; d0 += 32) {
                 const int d = d0 + lane;
@@ -683,7 +694,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     if (claim_n == 0) {
         if (sweeping) return;
         if (threadIdx.x == 0)
-            s_claim[3] = (atomicAdd(&qhead[nsm], 1) == (int)gridDim.x - 1 && ld_volatile(&qhead[nsm + 1]) < units) ? 1 : 0;
+            s_claim[3] = (atomicAdd(&qhead[nsm], 1) == (int)gridDim.x - 1 && ld_volatile(&qhead[nsm + 1]) < n_chunks * chunk) ? 1 : 0;
         __syncthreads();
         if (!s_claim[3]) return;
         sweeping = true;
@@ -693,7 +704,14 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     // wide launches rotate the warps over the entries from claim to claim so that partly filled CTAs of one SM do
     // not pile their warps on the same sub-partitions
     const int r_unit = S::kWide ? (warp + wpb - (claim_e / wpb) % wpb) % wpb : warp;
-    const int64_t base = r_unit < claim_n ? ((int64_t)claim_q + (int64_t)(claim_e + r_unit) * nsm) * PW : (int64_t)n_active;
+    int64_t base = n_active;
+    if (r_unit < claim_n) {
+        // entry e of queue t: chunk (e / chunk) * nsm + rank of t, unit e % chunk of it
+        const int e = claim_e + r_unit;
+        const int tq = claim_q - rot >= 0 ? claim_q - rot : claim_q - rot + nsm;
+        const int64_t unit = ((int64_t)(e / chunk) * nsm + tq) * chunk + e % chunk;
+        if (unit < units) base = unit * PW;
+    }
     if (base >= n_active) {
         if (lockstep)
             for (int step = 0; step < c_pr.gd_max_iters; ++step) __syncthreads();

@@ -136,6 +136,7 @@ struct SolveBuffers {
     int64_t first_problem_index;
     int32_t n_species;        // MemeticIkParams::num_threads: sub-problem sp = problem sp / n_species, species sp % n_species
     int32_t stop_on_first;    // MemeticIkParams::stop_on_first_soln
+    int32_t sm_rotation;      // first SM queue of this sub-batch's unit dealing (memetic_generation_kernel)
     // Philox4x32-10 key schedule of rng_seed: k0_r, k1_r for round r.  Per call (kernel parameter space, i.e.
     // constant-bank operands like the tables above), so that calls that differ only in the seed share one
     // parameter upload.
