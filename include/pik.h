@@ -39,11 +39,13 @@ enum {
 /* moveit_msgs::msg::MoveItErrorCodes values written by pick_ik_plugin.cpp:212,215 */
 enum { PIK_SUCCESS = 1, PIK_NO_IK_SOLUTION = -31 };
 
-enum { PIK_JOINT_FIXED = 0, PIK_JOINT_REVOLUTE = 1, PIK_JOINT_PRISMATIC = 2 };
+/* FLOATING: 7 variables x y z, quaternion x y z w; PLANAR: 3 variables x y theta (src/forward_kinematics.cpp:64-79) */
+enum { PIK_JOINT_FIXED = 0, PIK_JOINT_REVOLUTE = 1, PIK_JOINT_PRISMATIC = 2, PIK_JOINT_FLOATING = 3, PIK_JOINT_PLANAR = 4 };
+#define PIK_MAX_TIPS 4
 enum { PIK_MODE_GLOBAL = 0, PIK_MODE_LOCAL = 1 }; /* yaml `mode`: "global" | "local" */
 enum { PIK_MEM_HOST = 0, PIK_MEM_DEVICE = 1 };
 
-/* One joint of the serial chain model-root -> tip link, in chain order.  Replaces what
+/* One joint of the robot (serial chain: in chain order, model root -> tip link).  Replaces what
  * Robot::from (src/robot.cpp:44-85) and make_fk_fn (src/fk_moveit.cpp:11-35) read from the MoveIt
  * RobotModel: joint type, LinkModel::getJointOriginTransform, joint axis, VariableBounds. */
 typedef struct pik_joint_desc {
@@ -55,6 +57,9 @@ typedef struct pik_joint_desc {
     double min_position; /* VariableBounds::min_position_ / max_position_ (continuous: -pi / pi) */
     double max_position;
     double max_velocity; /* VariableBounds::max_velocity_, 0 = none */
+    /* FLOATING / PLANAR joints: bounded / min / max apply to the translation variables (MoveIt's default: unbounded);
+     * the quaternion components are bounded to [-1, 1] and the planar angle is unbounded, as MoveIt's joint models
+     * set them; max_velocity applies to every variable of the joint */
 } pik_joint_desc;
 
 /* Robot::Variable, include/pick_ik/robot.hpp:15-37 */
@@ -119,13 +124,31 @@ void pik_params_default(pik_params* p);
 /* the YAML validators (one_of / gt_eq) plus elite <= population and table limits */
 int pik_params_validate(const pik_params* p);
 
-/* Robot::from + chain flattening (src/robot.cpp:44-85; src/pick_ik_plugin.cpp:65-68) */
+/* Robot::from + chain flattening (src/robot.cpp:44-85; src/pick_ik_plugin.cpp:65-68): the serial chain model root ->
+ * tip link, joints in chain order, one tip behind the last joint */
 int pik_robot_create(const pik_joint_desc* joints, int32_t n_joints, pik_robot** out);
+/*
+ * The general form: a kinematic tree with n_tips tip links (src/pick_ik_plugin.cpp:60-68: one goal pose per tip frame,
+ * src/goal.cpp:80-89,163-175; FK of every tip as src/fk_moveit.cpp:20-34 returns it), floating / planar joints and mimic
+ * joints.
+ *   parent    [n_joints]  the joint whose child link joint j hangs on, -1 = the model root; parents precede children
+ *                         (NULL: a serial chain in joint order)
+ *   tip_joint [n_tips]    the joint whose child link is tip t (n_tips <= PIK_MAX_TIPS)
+ *   mimic_of  [n_joints]  the joint a mimic joint follows (value = mimic_factor * master + mimic_offset), -1 = none;
+ *                         NULL: no mimic joints.  Mimic joints own no variable (src/robot.cpp:145-147).
+ * Variables are numbered in joint order (floating: 7, planar: 3, revolute / prismatic: 1, fixed / mimic: 0).
+ * Robots the serial-chain kernels cannot express run on the tree kernels (pik_robot_chain_signature: "tree").
+ */
+int pik_robot_create_tree(const pik_joint_desc* joints, int32_t n_joints, const int32_t* parent, const int32_t* tip_joint,
+                          int32_t n_tips, const int32_t* mimic_of, const double* mimic_factor, const double* mimic_offset,
+                          pik_robot** out);
+int32_t pik_robot_num_tips(const pik_robot* robot);
 void pik_robot_destroy(pik_robot* robot);
 int32_t pik_robot_num_variables(const pik_robot* robot);
 int pik_robot_get_variable(const pik_robot* robot, int32_t i, pik_variable* out);
 /* name of the compiled chain signature the kernels will use for this robot (host; informational):
- * "generic", "all-z 7R, x-rotation origins (static)", "identity origins", "x-rotation origins", "y-rotation origins" */
+ * "generic", "all-z 7R, x-rotation origins (static)", "identity origins", "x-rotation origins", "y-rotation origins",
+ * "tree" */
 const char* pik_robot_chain_signature(const pik_robot* robot);
 /* Robot::is_valid_configuration, src/robot.cpp:97-105 (host) */
 int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q);
@@ -155,7 +178,7 @@ void pik_solver_destroy(pik_solver* solver);
  * (src/pick_ik_plugin.cpp:162-217): ik_memetic (src/ik_memetic.cpp:285-373, one species) when
  * mode == global, ik_gradient (src/ik_gradient.cpp:96-139) when mode == local, for B independent
  * problems.
- *   goal_pose  [B][7]  px py pz qw qx qy qz of the tip in the model frame (the goal_frames of
+ *   goal_pose  [B][n_tips][7]  px py pz qw qx qy qz of every tip in the model frame (the goal_frames of
  *                      pick_ik_plugin.cpp:88-94; quaternion used un-normalised like tf2::fromMsg)
  *   seed       [B][n] (seed_stride = n) or [n] (seed_stride = 0): ik_seed_state
  *   solution   [B][n]  genes on success, the seed on failure (pick_ik_plugin.cpp:213,216)
@@ -192,7 +215,7 @@ int pik_solver_query(pik_solver* solver);
  * Batched FK + cost + solution test: make_cost_fn (src/goal.cpp:188-203),
  * make_is_solution_test_fn (src/goal.cpp:163-186) and the tip frame of make_fk_fn
  * (src/fk_moveit.cpp:20-34) for B configurations q [B][n].  Outputs may be NULL.
- * tip_pose [B][7] = px py pz qw qx qy qz.
+ * goal_pose [B][n_tips][7]; tip_pose [B][n_tips][7] = px py pz qw qx qy qz of every tip.
  */
 int pik_eval_cost(pik_solver* solver, const pik_params* params, int64_t B, const double* goal_pose,
                   const double* seed, int64_t seed_stride, const double* q, double* cost,

@@ -12,6 +12,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
 MAX_VARS = 16
+MAX_STEPS = 16
+MAX_TIPS = 4
 
 
 def _source_hash() -> str:
@@ -44,13 +46,16 @@ class Variable(C.Structure):
 
 
 class Step(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("pad_", C.c_int32), ("sign", C.c_double), ("R", C.c_double * 9),
-                ("t", C.c_double * 3), ("axis", C.c_double * 3), ("axis_sq", C.c_double * 6)]
+    _fields_ = [("kind", C.c_int32), ("parent", C.c_int32), ("var0", C.c_int32), ("pad_", C.c_int32),
+                ("sign", C.c_double), ("R", C.c_double * 9), ("t", C.c_double * 3), ("axis", C.c_double * 3),
+                ("axis_sq", C.c_double * 6), ("mimic_factor", C.c_double), ("mimic_offset", C.c_double)]
 
 
 class Robot(C.Structure):
-    _fields_ = [("n", C.c_int32), ("has_tip", C.c_int32), ("steps", Step * MAX_VARS),
-                ("vars", Variable * MAX_VARS), ("tip_R", C.c_double * 9), ("tip_t", C.c_double * 3)]
+    _fields_ = [("n", C.c_int32), ("has_tip", C.c_int32), ("n_steps", C.c_int32), ("n_tips", C.c_int32),
+                ("steps", Step * MAX_STEPS), ("vars", Variable * MAX_VARS), ("tip_step", C.c_int32 * MAX_TIPS),
+                ("tip_has", C.c_int32 * MAX_TIPS), ("tip_R", (C.c_double * 9) * MAX_TIPS),
+                ("tip_t", (C.c_double * 3) * MAX_TIPS)]
 
 
 class Params(C.Structure):
@@ -68,8 +73,9 @@ class Params(C.Structure):
 
 
 class Problem(C.Structure):
-    _fields_ = [("robot", C.POINTER(Robot)), ("params", C.POINTER(Params)), ("goal_t", C.c_double * 3),
-                ("goal_R", C.c_double * 9), ("goal_q", C.c_double * 4), ("seed", C.c_double * MAX_VARS)]
+    _fields_ = [("robot", C.POINTER(Robot)), ("params", C.POINTER(Params)), ("goal_t", (C.c_double * 3) * MAX_TIPS),
+                ("goal_R", (C.c_double * 9) * MAX_TIPS), ("goal_q", (C.c_double * 4) * MAX_TIPS),
+                ("seed", C.c_double * MAX_VARS)]
 
 
 class Result(C.Structure):
@@ -144,6 +150,30 @@ def build_robot(joint_desc: np.ndarray) -> Robot:
     return r
 
 
+def build_robot_tree(joint_desc: np.ndarray, parent, tip_joint, mimic_of=None, mimic_factor=None,
+                     mimic_offset=None) -> Robot:
+    """Kinematic tree with several tips (and mimic joints): orc_robot_build_tree."""
+    r = Robot()
+    jd = np.ascontiguousarray(joint_desc)
+    n = len(jd)
+    par = np.ascontiguousarray(parent, dtype=np.int32)
+    tips = np.ascontiguousarray(tip_joint, dtype=np.int32)
+    assert par.shape == (n,)
+    mo = mf = mb = None
+    if mimic_of is not None:
+        mo = np.ascontiguousarray(mimic_of, dtype=np.int32)
+        mf = np.ascontiguousarray(mimic_factor, dtype=np.float64)
+        mb = np.ascontiguousarray(mimic_offset, dtype=np.float64)
+    vp = C.c_void_p
+    rc = lib().orc_robot_build_tree(jd.ctypes.data_as(vp), C.c_int(n), par.ctypes.data_as(vp), tips.ctypes.data_as(vp),
+                                    C.c_int(len(tips)), None if mo is None else mo.ctypes.data_as(vp),
+                                    None if mf is None else mf.ctypes.data_as(vp),
+                                    None if mb is None else mb.ctypes.data_as(vp), C.byref(r))
+    if rc != 0:
+        raise ValueError(f"orc_robot_build_tree failed: {rc}")
+    return r
+
+
 def sincos(x: float):
     s, c = C.c_double(), C.c_double()
     lib().orc_sincos(float(x), C.byref(s), C.byref(c))
@@ -206,6 +236,14 @@ def pose_from_fk(robot: Robot, q) -> np.ndarray:
     return pose
 
 
+def poses_from_fk(robot: Robot, q) -> np.ndarray:
+    """[n_tips, 7] poses of all tips."""
+    qa = np.ascontiguousarray(np.asarray(q, dtype=np.float64))
+    pose = np.zeros((robot.n_tips, 7))
+    lib().orc_poses_from_fk(C.byref(robot), _dp(qa), _dp(pose.reshape(-1)))
+    return pose
+
+
 def random_configuration(robot: Robot, gen_seed: int, problem_index: int) -> np.ndarray:
     q = np.zeros(robot.n)
     lib().orc_random_configuration(C.byref(robot), C.c_uint64(gen_seed), C.c_uint32(problem_index), _dp(q))
@@ -250,6 +288,7 @@ def solve_batch(robot: Robot, params: Params, goal_pose: np.ndarray, seed: np.nd
     """Returns dict(solution [B,n], error_code [B], cost [B], iterations [B], evals)."""
     goal_pose = np.ascontiguousarray(goal_pose, dtype=np.float64)
     B = goal_pose.shape[0]
+    assert goal_pose.size == B * robot.n_tips * 7, "goal_pose must be [B, n_tips, 7]"
     n = robot.n
     seed = np.ascontiguousarray(seed, dtype=np.float64)
     stride = 0 if seed.ndim == 1 or seed.shape[0] == 1 else n
@@ -258,7 +297,7 @@ def solve_batch(robot: Robot, params: Params, goal_pose: np.ndarray, seed: np.nd
     cst = np.zeros(B)
     its = np.zeros(B, dtype=np.int32)
     ev = C.c_uint64(0)
-    lib().orc_solve_batch(C.byref(robot), C.byref(params), B, first_problem_index, _dp(goal_pose),
+    lib().orc_solve_batch(C.byref(robot), C.byref(params), B, first_problem_index, _dp(goal_pose.reshape(-1)),
                           _dp(seed.reshape(-1)), stride, _dp(sol.reshape(-1)), _ip(err), _dp(cst), _ip(its),
                           C.byref(ev), n_threads)
     return dict(solution=sol, error_code=err, cost=cst, iterations=its, evals=ev.value)
@@ -272,15 +311,21 @@ def eval_cost_batch(robot: Robot, params: Params, goal_pose: np.ndarray, seed: n
     stride = 0 if seed.ndim == 1 or seed.shape[0] == 1 else n
     cst = np.zeros(B)
     sol = np.zeros(B, dtype=np.int32)
-    tip = np.zeros((B, 7))
-    lib().orc_eval_cost_batch(C.byref(robot), C.byref(params), B, _dp(goal_pose), _dp(seed.reshape(-1)), stride,
+    assert goal_pose.size == B * robot.n_tips * 7, "goal_pose must be [B, n_tips, 7]"
+    tip = np.zeros((B, 7)) if robot.n_tips == 1 else np.zeros((B, robot.n_tips, 7))
+    lib().orc_eval_cost_batch(C.byref(robot), C.byref(params), B, _dp(goal_pose.reshape(-1)), _dp(seed.reshape(-1)), stride,
                               _dp(q.reshape(-1)), _dp(cst), _ip(sol), _dp(tip.reshape(-1)))
     return cst, sol, tip
 
 
 def make_targets(robot: Robot, B: int, gen_seed: int = 0xC0FFEE, first: int = 0) -> np.ndarray:
     """target b = FK(q*_b), q*_b ~ U(limits) from Philox stream (gen_seed, b)."""
-    out = np.zeros((B, 7))
+    if robot.n_tips == 1:
+        out = np.zeros((B, 7))
+        for b in range(B):
+            out[b] = pose_from_fk(robot, random_configuration(robot, gen_seed, first + b))
+        return out
+    out = np.zeros((B, robot.n_tips, 7))
     for b in range(B):
-        out[b] = pose_from_fk(robot, random_configuration(robot, gen_seed, first + b))
+        out[b] = poses_from_fk(robot, random_configuration(robot, gen_seed, first + b))
     return out

@@ -345,17 +345,31 @@ static void mat_vec_add(const double A[9], const double v[3], const double t[3],
         out[r] = fma(A[3 * r + 2], v[2], fma(A[3 * r + 1], v[1], fma(A[3 * r], v[0], t[r])));
 }
 
-int orc_robot_build(const orc_joint_desc* joints, int n_joints, orc_robot* out) {
-    memset(out, 0, sizeof(*out));
-    double accR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, acct[3] = {0, 0, 0};
-    int have_acc = 0, n = 0;
-    for (int j = 0; j < n_joints; ++j) {
-        const orc_joint_desc* jd = &joints[j];
-        /* acc = acc * origin_j */
-        if (!have_acc) {
-            memcpy(accR, jd->origin_R, sizeof(accR));
-            memcpy(acct, jd->origin_t, sizeof(acct));
-            have_acc = 1;
+static void fill_variable(orc_variable* v, int bounded, double lo, double hi, double max_velocity) {
+    /* Robot::from, robot.cpp:52-72 */
+    v->bounded = bounded;
+    v->min = lo;
+    v->max = hi;
+    v->mid = 0.5 * (v->min + v->max);
+    v->half_span = v->bounded ? (v->max - v->min) / 2.0 : M_PI;
+    v->max_velocity_rcp = max_velocity > 0.0 ? 1.0 / max_velocity : 0.0;
+}
+
+/* acc <- product, root to leaf, of the origins of the fixed joints between joint j and its nearest moving
+ * ancestor (exclusive), then the origin of j itself.  Returns that ancestor (-1: the model root). */
+static int fold_origins(const orc_joint_desc* joints, const int32_t* parent, int j, double accR[9], double acct[3]) {
+    int path[64], np = 0;
+    path[np++] = j;
+    int k = parent ? parent[j] : j - 1;
+    while (k >= 0 && joints[k].type == ORC_JOINT_FIXED && np < 64) {
+        path[np++] = k;
+        k = parent ? parent[k] : k - 1;
+    }
+    for (int a = np - 1; a >= 0; --a) {
+        const orc_joint_desc* jd = &joints[path[a]];
+        if (a == np - 1) {
+            memcpy(accR, jd->origin_R, 9 * sizeof(double));
+            memcpy(acct, jd->origin_t, 3 * sizeof(double));
         } else {
             double nR[9], nt[3];
             mat_vec_add(accR, jd->origin_t, acct, nt);
@@ -363,16 +377,34 @@ int orc_robot_build(const orc_joint_desc* joints, int n_joints, orc_robot* out) 
             memcpy(accR, nR, sizeof(nR));
             memcpy(acct, nt, sizeof(nt));
         }
+    }
+    return k;
+}
+
+int orc_robot_build_tree(const orc_joint_desc* joints, int n_joints, const int32_t* parent,
+                         const int32_t* tip_joint, int n_tips, const int32_t* mimic_of,
+                         const double* mimic_factor, const double* mimic_offset, orc_robot* out) {
+    memset(out, 0, sizeof(*out));
+    if (n_joints <= 0 || n_joints > 64 || n_tips < 1 || n_tips > ORC_MAX_TIPS) return -1;
+    int step_of[64], n = 0, ns = 0;
+    double max_velocity[ORC_MAX_VARS];
+    for (int j = 0; j < n_joints; ++j) {
+        const orc_joint_desc* jd = &joints[j];
+        step_of[j] = -1;
+        if (parent && !(parent[j] >= -1 && parent[j] < j)) return -4; /* parents precede children */
         if (jd->type == ORC_JOINT_FIXED) continue;
-        if (n >= ORC_MAX_VARS) return -1;
-        orc_step* st = &out->steps[n];
-        memcpy(st->R, accR, sizeof(accR));
-        memcpy(st->t, acct, sizeof(acct));
+        if (ns >= ORC_MAX_STEPS) return -1;
+        orc_step* st = &out->steps[ns];
+        const int up = fold_origins(joints, parent, j, st->R, st->t);
+        st->parent = up >= 0 ? step_of[up] : -1;
         memcpy(st->axis, jd->axis, sizeof(st->axis));
         double x = jd->axis[0], y = jd->axis[1], z = jd->axis[2];
         st->axis_sq[0] = x * x; st->axis_sq[1] = y * y; st->axis_sq[2] = z * z;
         st->axis_sq[3] = x * y; st->axis_sq[4] = x * z; st->axis_sq[5] = y * z;
         st->sign = 1.0;
+        st->mimic_factor = 1.0;
+        st->mimic_offset = 0.0;
+        int n_vars = 1;
         if (jd->type == ORC_JOINT_PRISMATIC) {
             st->kind = ORC_STEP_PRISMATIC;
         } else if (jd->type == ORC_JOINT_REVOLUTE) {
@@ -380,26 +412,57 @@ int orc_robot_build(const orc_joint_desc* joints, int n_joints, orc_robot* out) 
             if (fabs(x) == 1.0 && y == 0.0 && z == 0.0) { st->kind = ORC_STEP_REV_X; st->sign = x; }
             if (x == 0.0 && fabs(y) == 1.0 && z == 0.0) { st->kind = ORC_STEP_REV_Y; st->sign = y; }
             if (x == 0.0 && y == 0.0 && fabs(z) == 1.0) { st->kind = ORC_STEP_REV_Z; st->sign = z; }
+        } else if (jd->type == ORC_JOINT_FLOATING) {
+            st->kind = ORC_STEP_FLOATING;
+            n_vars = 7;
+        } else if (jd->type == ORC_JOINT_PLANAR) {
+            st->kind = ORC_STEP_PLANAR;
+            n_vars = 3;
         } else {
             return -2;
         }
-        /* Robot::from, robot.cpp:52-72 */
-        orc_variable* v = &out->vars[n];
-        v->bounded = jd->bounded;
-        v->min = jd->min_position;
-        v->max = jd->max_position;
-        v->mid = 0.5 * (v->min + v->max);
-        v->half_span = v->bounded ? (v->max - v->min) / 2.0 : M_PI;
-        v->max_velocity_rcp = jd->max_velocity > 0.0 ? 1.0 / jd->max_velocity : 0.0;
-        ++n;
-        have_acc = 0;
+        const int m = mimic_of ? mimic_of[j] : -1;
+        if (m >= 0) {
+            /* a mimic joint follows the variable of its master and owns none (robot.cpp:145-147) */
+            if (n_vars != 1 || m >= j || step_of[m] < 0 || joints[m].type > ORC_JOINT_PRISMATIC) return -5;
+            st->var0 = out->steps[step_of[m]].var0;
+            st->mimic_factor = mimic_factor[j] * out->steps[step_of[m]].mimic_factor;
+            st->mimic_offset = mimic_factor[j] * out->steps[step_of[m]].mimic_offset + mimic_offset[j];
+        } else {
+            if (n + n_vars > ORC_MAX_VARS) return -1;
+            st->var0 = n;
+            /* variable bounds as MoveIt's joint models set them: the translation variables of floating / planar
+             * joints take the description's bounds (unbounded by default), quaternion components [-1, 1], the
+             * planar angle is unbounded with the nominal range -pi .. pi */
+            for (int k = 0; k < n_vars; ++k) {
+                int bounded = jd->bounded;
+                double lo = jd->min_position, hi = jd->max_position;
+                if (jd->type == ORC_JOINT_FLOATING && k >= 3) { bounded = 1; lo = -1.0; hi = 1.0; }
+                if (jd->type == ORC_JOINT_PLANAR && k == 2) { bounded = 0; lo = -M_PI; hi = M_PI; }
+                fill_variable(&out->vars[n + k], bounded, lo, hi, jd->max_velocity);
+                max_velocity[n + k] = jd->max_velocity;
+            }
+            n += n_vars;
+        }
+        step_of[j] = ns++;
     }
+    if (n == 0) return -3;
     out->n = n;
-    out->has_tip = have_acc;
-    if (have_acc) {
-        memcpy(out->tip_R, accR, sizeof(accR));
-        memcpy(out->tip_t, acct, sizeof(acct));
+    out->n_steps = ns;
+    out->n_tips = n_tips;
+    for (int t = 0; t < n_tips; ++t) {
+        const int j = tip_joint[t];
+        if (j < 0 || j >= n_joints) return -6;
+        if (joints[j].type != ORC_JOINT_FIXED) {
+            out->tip_step[t] = step_of[j];
+            out->tip_has[t] = 0;
+        } else {
+            const int up = fold_origins(joints, parent, j, out->tip_R[t], out->tip_t[t]);
+            out->tip_step[t] = up >= 0 ? step_of[up] : -1;
+            out->tip_has[t] = 1;
+        }
     }
+    out->has_tip = out->tip_has[0];
     /* robot.cpp:69-82 */
     double divisor = 0.0;
     for (int i = 0; i < n; ++i) {
@@ -409,7 +472,13 @@ int orc_robot_build(const orc_joint_desc* joints, int n_joints, orc_robot* out) 
     if (divisor > 0.0)
         for (int i = 0; i < n; ++i)
             out->vars[i].minimal_displacement_factor = out->vars[i].max_velocity_rcp / divisor;
-    return n > 0 ? 0 : -3;
+    (void)max_velocity;
+    return 0;
+}
+
+int orc_robot_build(const orc_joint_desc* joints, int n_joints, orc_robot* out) {
+    const int32_t tip = n_joints - 1;
+    return orc_robot_build_tree(joints, n_joints, NULL, &tip, 1, NULL, NULL, NULL, out);
 }
 
 /* Rotate columns (a, b) of R: the product R * Rot_axis(angle) for an axis-aligned joint.
@@ -422,10 +491,35 @@ static void rotate_cols(double R[9], int a, int b, double s, double c) {
     }
 }
 
-/* One moving joint applied to frame (R, t) that already includes the folded origin.
- * Revolute: RevoluteJointModel::computeTransform (same rotation as
- * forward_kinematics.cpp:48-57); prismatic: forward_kinematics.cpp:58-63. */
-static void apply_joint(const orc_step* st, double q, double R[9], double t[3]) {
+/* One moving joint applied to frame (R, t) that already includes the folded origin; qv = the variables of the
+ * joint.  Revolute: RevoluteJointModel::computeTransform (same rotation as
+ * forward_kinematics.cpp:48-57); prismatic: forward_kinematics.cpp:58-63; floating:
+ * Translation3d(v0 v1 v2) * Quaterniond(w = v6, x = v3, y = v4, z = v5), quaternion used as given
+ * (forward_kinematics.cpp:64-70); planar: Translation3d(x, y, 0) * rotation about z by theta (what
+ * PlanarJointModel::computeTransform returns, forward_kinematics.cpp:71-79). */
+static void apply_joint(const orc_step* st, const double* qv, double R[9], double t[3]) {
+    if (st->kind == ORC_STEP_FLOATING || st->kind == ORC_STEP_PLANAR) {
+        double J[9], d[3], nR[9], nt[3];
+        if (st->kind == ORC_STEP_FLOATING) {
+            const double quat[4] = {qv[6], qv[3], qv[4], qv[5]};
+            orc_quat_to_matrix(quat, J);
+            d[0] = qv[0]; d[1] = qv[1]; d[2] = qv[2];
+        } else {
+            double s, c;
+            orc_sincos(qv[2], &s, &c);
+            J[0] = c; J[1] = -s; J[2] = 0.0;
+            J[3] = s; J[4] = c; J[5] = 0.0;
+            J[6] = 0.0; J[7] = 0.0; J[8] = 1.0;
+            d[0] = qv[0]; d[1] = qv[1]; d[2] = 0.0;
+        }
+        mat_vec_add(R, d, t, nt);
+        mat_mul(R, J, nR);
+        memcpy(R, nR, sizeof(nR));
+        memcpy(t, nt, sizeof(nt));
+        return;
+    }
+    /* (a joint that is not a mimic has factor 1 and offset 0: the value is the variable itself) */
+    const double q = (st->mimic_factor == 1.0 && st->mimic_offset == 0.0) ? qv[0] : qv[0] * st->mimic_factor + st->mimic_offset;
     if (st->kind == ORC_STEP_PRISMATIC) {
         double d[3] = {st->axis[0] * q, st->axis[1] * q, st->axis[2] * q};
         double nt[3];
@@ -459,27 +553,45 @@ static void apply_joint(const orc_step* st, double q, double R[9], double t[3]) 
     }
 }
 
-/* fk_moveit.cpp:20-34 -> tip frame of the chain.  Chain walk left to right. */
+/* fk_moveit.cpp:20-34 -> the tip frames.  Every link frame = parent link frame * folded origin * joint motion,
+ * root to leaf (RobotState::updateLinkTransforms). */
+void orc_fk_tips(const orc_robot* robot, const double* q, double* R_out, double* t_out) {
+    double FR[ORC_MAX_STEPS][9], FT[ORC_MAX_STEPS][3];
+    for (int k = 0; k < robot->n_steps; ++k) {
+        const orc_step* st = &robot->steps[k];
+        if (st->parent < 0) {
+            memcpy(FR[k], st->R, 9 * sizeof(double));
+            memcpy(FT[k], st->t, 3 * sizeof(double));
+        } else {
+            mat_vec_add(FR[st->parent], st->t, FT[st->parent], FT[k]);
+            mat_mul(FR[st->parent], st->R, FR[k]);
+        }
+        apply_joint(st, q + st->var0, FR[k], FT[k]);
+    }
+    for (int i = 0; i < robot->n_tips; ++i) {
+        double* R = R_out + 9 * i;
+        double* t = t_out + 3 * i;
+        const int k = robot->tip_step[i];
+        if (k < 0) { /* a tip the group does not move: the constant transform from the model root */
+            static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            memcpy(R, robot->tip_has[i] ? robot->tip_R[i] : I, 9 * sizeof(double));
+            t[0] = t[1] = t[2] = 0.0;
+            if (robot->tip_has[i]) memcpy(t, robot->tip_t[i], 3 * sizeof(double));
+        } else if (robot->tip_has[i]) {
+            mat_vec_add(FR[k], robot->tip_t[i], FT[k], t);
+            mat_mul(FR[k], robot->tip_R[i], R);
+        } else {
+            memcpy(R, FR[k], 9 * sizeof(double));
+            memcpy(t, FT[k], 3 * sizeof(double));
+        }
+    }
+}
+
 void orc_fk(const orc_robot* robot, const double* q, double R[9], double t[3]) {
-    memcpy(R, robot->steps[0].R, 9 * sizeof(double));
-    memcpy(t, robot->steps[0].t, 3 * sizeof(double));
-    apply_joint(&robot->steps[0], q[0], R, t);
-    for (int j = 1; j < robot->n; ++j) {
-        const orc_step* st = &robot->steps[j];
-        double nR[9], nt[3];
-        mat_vec_add(R, st->t, t, nt);
-        mat_mul(R, st->R, nR);
-        memcpy(R, nR, sizeof(nR));
-        memcpy(t, nt, sizeof(nt));
-        apply_joint(st, q[j], R, t);
-    }
-    if (robot->has_tip) {
-        double nR[9], nt[3];
-        mat_vec_add(R, robot->tip_t, t, nt);
-        mat_mul(R, robot->tip_R, nR);
-        memcpy(R, nR, sizeof(nR));
-        memcpy(t, nt, sizeof(nt));
-    }
+    double Rs[ORC_MAX_TIPS][9], ts[ORC_MAX_TIPS][3];
+    orc_fk_tips(robot, q, &Rs[0][0], &ts[0][0]);
+    memcpy(R, Rs[0], 9 * sizeof(double));
+    memcpy(t, ts[0], 3 * sizeof(double));
 }
 
 /* robot.cpp:36-42 (std::clamp(v, lo, hi) = v < lo ? lo : hi < v ? hi : v) */
@@ -543,14 +655,18 @@ void orc_params_default(orc_params* p) {
 }
 
 void orc_problem_init(orc_problem* pb, const orc_robot* robot, const orc_params* params,
-                      const double goal_pose[7], const double* seed) {
+                      const double* goal_pose, const double* seed) {
+    memset(pb, 0, sizeof(*pb));
     pb->robot = robot;
     pb->params = params;
-    pb->goal_t[0] = goal_pose[0];
-    pb->goal_t[1] = goal_pose[1];
-    pb->goal_t[2] = goal_pose[2];
-    orc_quat_to_matrix(goal_pose + 3, pb->goal_R);     /* tf2::fromMsg, robot.cpp:175-176 */
-    orc_matrix_to_quat(pb->goal_R, pb->goal_q);        /* goal.cpp:22 */
+    for (int i = 0; i < robot->n_tips; ++i) {
+        const double* gp = goal_pose + 7 * i;
+        pb->goal_t[i][0] = gp[0];
+        pb->goal_t[i][1] = gp[1];
+        pb->goal_t[i][2] = gp[2];
+        orc_quat_to_matrix(gp + 3, pb->goal_R[i]);      /* tf2::fromMsg, robot.cpp:175-176 */
+        orc_matrix_to_quat(pb->goal_R[i], pb->goal_q[i]); /* goal.cpp:22 */
+    }
     for (int i = 0; i < ORC_MAX_VARS; ++i) pb->seed[i] = (i < robot->n) ? seed[i] : 0.0;
 }
 
@@ -608,10 +724,12 @@ static int goal_costs(const orc_problem* pb, const double* q, double out[3]) {
 
 /* goal.cpp:188-203 */
 double orc_cost(const orc_problem* pb, const double* q) {
-    double R[9], t[3];
-    orc_fk(pb->robot, q, R, t);
-    double pose_cost = 0.0 + pose_cost_q(pb->goal_t, pb->goal_q, t, R, pb->params->position_scale,
-                                         pb->params->rotation_scale);
+    double R[ORC_MAX_TIPS][9], t[ORC_MAX_TIPS][3];
+    orc_fk_tips(pb->robot, q, &R[0][0], &t[0][0]);
+    double pose_cost = 0.0; /* std::accumulate over the tips, goal.cpp:192-196 */
+    for (int i = 0; i < pb->robot->n_tips; ++i)
+        pose_cost = pose_cost + pose_cost_q(pb->goal_t[i], pb->goal_q[i], t[i], R[i], pb->params->position_scale,
+                                            pb->params->rotation_scale);
     double g[3];
     int ng = goal_costs(pb, q, g);
     double goal_cost = 0.0;
@@ -622,13 +740,15 @@ double orc_cost(const orc_problem* pb, const double* q) {
 /* goal.cpp:163-186 with thresholds enabled as pick_ik_plugin.cpp:97-106 */
 int orc_is_solution(const orc_problem* pb, const double* q) {
     const orc_params* p = pb->params;
-    double R[9], t[3];
-    orc_fk(pb->robot, q, R, t);
-    if (p->position_scale > 0.0 && !(orc_linear_distance(pb->goal_t, t) <= p->position_threshold))
-        return 0;
-    if (p->rotation_scale > 0.0 &&
-        !(fabs(orc_angular_distance_q(pb->goal_q, R)) <= p->orientation_threshold))
-        return 0;
+    double R[ORC_MAX_TIPS][9], t[ORC_MAX_TIPS][3];
+    orc_fk_tips(pb->robot, q, &R[0][0], &t[0][0]);
+    for (int i = 0; i < pb->robot->n_tips; ++i) { /* every frame test, goal.cpp:169-175 */
+        if (p->position_scale > 0.0 && !(orc_linear_distance(pb->goal_t[i], t[i]) <= p->position_threshold))
+            return 0;
+        if (p->rotation_scale > 0.0 &&
+            !(fabs(orc_angular_distance_q(pb->goal_q[i], R[i])) <= p->orientation_threshold))
+            return 0;
+    }
     double thr_sq = p->cost_threshold * p->cost_threshold;
     double g[3];
     int ng = goal_costs(pb, q, g);
@@ -1150,7 +1270,7 @@ static void solve_one(batch_job* job, int64_t b, uint64_t* evals) {
     const int n = job->robot->n;
     const double* seed = job->seed + b * job->seed_stride;
     orc_problem pb;
-    orc_problem_init(&pb, job->robot, job->params, job->goal_pose + 7 * b, seed);
+    orc_problem_init(&pb, job->robot, job->params, job->goal_pose + 7 * job->robot->n_tips * b, seed);
     orc_result res;
     if (job->params->mode == 0 && job->params->memetic_num_threads > 1)
         orc_ik_memetic_species(&pb, seed, (uint32_t)(job->first + b), job->params->memetic_num_threads,
@@ -1213,18 +1333,13 @@ void orc_solve_batch(const orc_robot* robot, const orc_params* params, int64_t B
 void orc_eval_cost_batch(const orc_robot* robot, const orc_params* params, int64_t B,
                          const double* goal_pose, const double* seed, int64_t seed_stride,
                          const double* q, double* cost, int32_t* is_solution, double* tip_pose) {
-    const int n = robot->n;
+    const int n = robot->n, T = robot->n_tips;
     for (int64_t b = 0; b < B; ++b) {
         orc_problem pb;
-        orc_problem_init(&pb, robot, params, goal_pose + 7 * b, seed + b * seed_stride);
+        orc_problem_init(&pb, robot, params, goal_pose + 7 * T * b, seed + b * seed_stride);
         if (cost) cost[b] = orc_cost(&pb, q + b * n);
         if (is_solution) is_solution[b] = orc_is_solution(&pb, q + b * n);
-        if (tip_pose) {
-            double R[9], t[3];
-            orc_fk(robot, q + b * n, R, t);
-            tip_pose[7 * b + 0] = t[0]; tip_pose[7 * b + 1] = t[1]; tip_pose[7 * b + 2] = t[2];
-            orc_matrix_to_quat(R, tip_pose + 7 * b + 3);
-        }
+        if (tip_pose) orc_poses_from_fk(robot, q + b * n, tip_pose + 7 * T * b);
     }
 }
 
@@ -1239,6 +1354,15 @@ void orc_random_configuration(const orc_robot* robot, uint64_t gen_seed, uint32_
         if ((i & 1) == 0) stream_block(&st, (uint32_t)(i >> 1), w);
         uint32_t lo = w[2 * (i & 1)], hi = w[2 * (i & 1) + 1];
         q[i] = v->bounded ? uniform_real_words(v->min, v->max, lo, hi) : uniform_real_words(-M_PI, M_PI, lo, hi);
+    }
+}
+
+void orc_poses_from_fk(const orc_robot* robot, const double* q, double* pose) {
+    double R[ORC_MAX_TIPS][9], t[ORC_MAX_TIPS][3];
+    orc_fk_tips(robot, q, &R[0][0], &t[0][0]);
+    for (int i = 0; i < robot->n_tips; ++i) {
+        pose[7 * i + 0] = t[i][0]; pose[7 * i + 1] = t[i][1]; pose[7 * i + 2] = t[i][2];
+        orc_matrix_to_quat(R[i], pose + 7 * i + 3);
     }
 }
 

@@ -40,9 +40,13 @@ extern "C" {
 #endif
 
 #define ORC_MAX_VARS 16
+#define ORC_MAX_STEPS 16
+#define ORC_MAX_TIPS 4
 
-/* joint kinds in a chain description (before folding of fixed joints) */
-enum { ORC_JOINT_FIXED = 0, ORC_JOINT_REVOLUTE = 1, ORC_JOINT_PRISMATIC = 2 };
+/* joint kinds in a robot description (before folding of fixed joints).  FLOATING (7 variables: x y z, quaternion
+ * x y z w) and PLANAR (3 variables: x y theta) follow forward_kinematics.cpp:64-79. */
+enum { ORC_JOINT_FIXED = 0, ORC_JOINT_REVOLUTE = 1, ORC_JOINT_PRISMATIC = 2, ORC_JOINT_FLOATING = 3,
+       ORC_JOINT_PLANAR = 4 };
 
 /* Same memory layout as pik_joint_desc in include/pik.h (both are filled from the same fixtures). */
 typedef struct {
@@ -68,25 +72,35 @@ typedef struct {
 
 /* step kinds after folding: which joint motion follows the folded constant origin */
 enum { ORC_STEP_REV_X = 0, ORC_STEP_REV_Y = 1, ORC_STEP_REV_Z = 2, ORC_STEP_REV_GENERAL = 3,
-       ORC_STEP_PRISMATIC = 4 };
+       ORC_STEP_PRISMATIC = 4, ORC_STEP_FLOATING = 8, ORC_STEP_PLANAR = 9 };
 
+/* One moving joint of the kinematic tree.  What FK returns for the tips is what MoveIt's
+ * RobotState::updateLinkTransforms computes (fk_moveit.cpp:20-34): the frame of a joint's child link =
+ * frame of the parent link * joint origin * joint motion, walked root to leaf. */
 typedef struct {
     int32_t kind;
+    int32_t parent; /* step whose frame the folded origin is applied to; -1 = the model root */
+    int32_t var0;   /* first variable of the joint (a mimic joint: the variable of the joint it follows) */
     int32_t pad_;
     double sign;  /* +1 / -1 for axis-aligned revolute (rotation about -axis = angle negated) */
-    double R[9];  /* folded constant origin: product of the fixed transforms since the previous */
+    double R[9];  /* folded constant origin: product of the fixed transforms since the parent  */
     double t[3];  /* moving joint, times this joint's origin                                   */
     double axis[3];
     double axis_sq[6]; /* xx, yy, zz, xy, xz, yz (cached like RevoluteJointModel::setAxis) */
+    double mimic_factor, mimic_offset; /* joint value = q[var0] * factor + offset (1, 0 unless a mimic joint) */
 } orc_step;
 
 typedef struct {
-    int32_t n;  /* active variables = moving joints on the chain */
-    int32_t has_tip; /* trailing fixed transform(s) after the last moving joint */
-    orc_step steps[ORC_MAX_VARS];
+    int32_t n;       /* active variables (robot.cpp:122-160: the non-mimic joints below the tips) */
+    int32_t has_tip; /* serial chains: tip_has[0] */
+    int32_t n_steps; /* moving joints, parents before children */
+    int32_t n_tips;
+    orc_step steps[ORC_MAX_STEPS];
     orc_variable vars[ORC_MAX_VARS];
-    double tip_R[9];
-    double tip_t[3];
+    int32_t tip_step[ORC_MAX_TIPS]; /* step the tip link hangs on (-1: the model root) */
+    int32_t tip_has[ORC_MAX_TIPS];  /* fixed transform(s) between that step and the tip link */
+    double tip_R[ORC_MAX_TIPS][9];
+    double tip_t[ORC_MAX_TIPS][3];
 } orc_robot;
 
 /* Mirror of the YAML parameter set (src/pick_ik_parameters.yaml) + solver structs. */
@@ -115,13 +129,14 @@ typedef struct {
     uint64_t rng_seed;
 } orc_params;
 
-/* One IK problem: robot + goal frame + seed state (for minimal displacement) + params */
+/* One IK problem: robot + one goal frame per tip (goal.cpp:80-89, assert at goal.cpp:169) + seed state (for
+ * minimal displacement) + params */
 typedef struct {
     const orc_robot* robot;
     const orc_params* params;
-    double goal_t[3];
-    double goal_R[9];
-    double goal_q[4]; /* Quaterniond(goal_R): w,x,y,z */
+    double goal_t[ORC_MAX_TIPS][3];
+    double goal_R[ORC_MAX_TIPS][9];
+    double goal_q[ORC_MAX_TIPS][4]; /* Quaterniond(goal_R): w,x,y,z */
     double seed[ORC_MAX_VARS];
 } orc_problem;
 
@@ -144,15 +159,26 @@ double orc_pose_cost(const double goal_t[3], const double goal_R[9], const doubl
                      const double tip_R[9], double position_scale, double rotation_scale);
 
 /* ---- robot ---- */
+/* serial chain model root -> tip: joints in chain order, one tip behind the last joint */
 int orc_robot_build(const orc_joint_desc* joints, int n_joints, orc_robot* out);
+/* kinematic tree with several tips.  parent[j]: the joint whose child link joint j hangs on (-1: the model root;
+ * parents precede children); tip_joint[t]: the joint whose child link is tip t; mimic_of[j] (or NULL): the joint a
+ * mimic joint follows, value = factor * master + offset (mimic joints contribute no variable, robot.cpp:145-147).
+ * Variables are numbered in joint order. */
+int orc_robot_build_tree(const orc_joint_desc* joints, int n_joints, const int32_t* parent,
+                         const int32_t* tip_joint, int n_tips, const int32_t* mimic_of,
+                         const double* mimic_factor, const double* mimic_offset, orc_robot* out);
+/* frame of tip 0 */
 void orc_fk(const orc_robot* robot, const double* q, double R[9], double t[3]);
+/* frames of all tips: R [n_tips][9], t [n_tips][3] */
+void orc_fk_tips(const orc_robot* robot, const double* q, double* R, double* t);
 double orc_clamp_to_limits(const orc_variable* v, double val);
 int orc_is_valid_configuration(const orc_robot* robot, const double* q);
 
 /* ---- goals / cost ---- */
 void orc_params_default(orc_params* p);
 void orc_problem_init(orc_problem* pb, const orc_robot* robot, const orc_params* params,
-                      const double goal_pose[7] /* px py pz qw qx qy qz */, const double* seed);
+                      const double* goal_pose /* [n_tips][7]: px py pz qw qx qy qz */, const double* seed);
 double orc_center_joints_cost(const orc_robot* robot, const double* q);
 double orc_avoid_joint_limits_cost(const orc_robot* robot, const double* q);
 double orc_minimal_displacement_cost(const orc_robot* robot, const double* q, const double* seed);
@@ -182,13 +208,13 @@ void orc_ik_memetic_species(const orc_problem* pb, const double* initial_guess, 
                             int n_species, int stop_on_first, orc_result* out);
 
 /* Batch driver = plugin mapping (pick_ik_plugin.cpp:209-217): error_code 1 / -31, solution = seed on
- * failure.  seed_stride = 0 broadcasts one seed.  n_threads <= 0: all cores. */
+ * failure.  goal_pose [B][n_tips][7].  seed_stride = 0 broadcasts one seed.  n_threads <= 0: all cores. */
 void orc_solve_batch(const orc_robot* robot, const orc_params* params, int64_t B,
                      int64_t first_problem_index, const double* goal_pose, const double* seed,
                      int64_t seed_stride, double* solution, int32_t* error_code, double* cost,
                      int32_t* iterations, uint64_t* evals_total, int n_threads);
 
-/* Batched FK + cost (checker for pik_eval_cost): q [B][n], goal_pose [B][7] */
+/* Batched FK + cost (checker for pik_eval_cost): q [B][n], goal_pose [B][n_tips][7], tip_pose [B][n_tips][7] */
 void orc_eval_cost_batch(const orc_robot* robot, const orc_params* params, int64_t B,
                          const double* goal_pose, const double* seed, int64_t seed_stride,
                          const double* q, double* cost, int32_t* is_solution, double* tip_pose);
@@ -196,7 +222,8 @@ void orc_eval_cost_batch(const orc_robot* robot, const orc_params* params, int64
 /* Synthetic target generator: q* ~ U(limits) from Philox stream (gen_seed, b). */
 void orc_random_configuration(const orc_robot* robot, uint64_t gen_seed, uint32_t problem_index,
                               double* q);
-void orc_pose_from_fk(const orc_robot* robot, const double* q, double pose[7]);
+void orc_pose_from_fk(const orc_robot* robot, const double* q, double pose[7]);        /* tip 0 */
+void orc_poses_from_fk(const orc_robot* robot, const double* q, double* pose /* [n_tips][7] */);
 
 #ifdef __cplusplus
 }

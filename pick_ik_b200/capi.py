@@ -11,7 +11,7 @@ from typing import Optional
 
 import numpy as np
 
-from .robots import JOINT_DESC_DTYPE, RobotChain
+from .robots import JOINT_DESC_DTYPE, RobotChain, RobotTree
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PIK_LIB_PATH") or os.path.join(HERE, "libpik_b200.so")  # override: A/B experiments only
@@ -25,7 +25,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 # every symbol include/pik.h declares
 EXPORTS = [
     "pik_version", "pik_status_string", "pik_params_default", "pik_params_validate", "pik_robot_create",
-    "pik_robot_destroy", "pik_robot_num_variables", "pik_robot_get_variable",
+    "pik_robot_create_tree", "pik_robot_num_tips", "pik_robot_destroy", "pik_robot_num_variables", "pik_robot_get_variable",
     "pik_robot_is_valid_configuration", "pik_robot_chain_signature", "pik_random_configurations", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
     "pik_solve_batch_async", "pik_solver_wait", "pik_solver_query", "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
     "pik_device_count", "pik_host_alloc", "pik_host_free", "pik_measure_fp64_peak",
@@ -100,6 +100,9 @@ def lib() -> C.CDLL:
     L.pik_params_default.argtypes = [C.POINTER(Params)]
     L.pik_params_validate.argtypes = [C.POINTER(Params)]
     L.pik_robot_create.argtypes = [vp, C.c_int32, C.POINTER(vp)]
+    L.pik_robot_create_tree.argtypes = [vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, C.POINTER(vp)]
+    L.pik_robot_num_tips.restype = C.c_int32
+    L.pik_robot_num_tips.argtypes = [vp]
     L.pik_robot_destroy.restype = None
     L.pik_robot_destroy.argtypes = [vp]
     L.pik_robot_num_variables.restype = C.c_int32
@@ -171,15 +174,26 @@ class Robot:
     """pik_robot: the flattened chain + Robot::Variable table (src/robot.cpp:44-85)."""
 
     def __init__(self, chain_or_desc):
-        desc = chain_or_desc.joint_desc() if isinstance(chain_or_desc, RobotChain) else chain_or_desc
-        desc = np.ascontiguousarray(desc, dtype=JOINT_DESC_DTYPE)
-        self.desc = desc
         h = C.c_void_p()
-        rc = lib().pik_robot_create(desc.ctypes.data_as(C.c_void_p), len(desc), C.byref(h))
+        if isinstance(chain_or_desc, RobotTree):
+            desc, parent, tips, mimic_of, factor, offset = chain_or_desc.tree_arrays()
+            desc = np.ascontiguousarray(desc, dtype=JOINT_DESC_DTYPE)
+            vp = C.c_void_p
+            rc = lib().pik_robot_create_tree(desc.ctypes.data_as(vp), len(desc), parent.ctypes.data_as(vp),
+                                             tips.ctypes.data_as(vp), len(tips), mimic_of.ctypes.data_as(vp),
+                                             factor.ctypes.data_as(vp), offset.ctypes.data_as(vp), C.byref(h))
+            where = "pik_robot_create_tree"
+        else:
+            desc = chain_or_desc.joint_desc() if isinstance(chain_or_desc, RobotChain) else chain_or_desc
+            desc = np.ascontiguousarray(desc, dtype=JOINT_DESC_DTYPE)
+            rc = lib().pik_robot_create(desc.ctypes.data_as(C.c_void_p), len(desc), C.byref(h))
+            where = "pik_robot_create"
+        self.desc = desc
         if rc != PIK_OK:
-            raise PikError(rc, "pik_robot_create")
+            raise PikError(rc, where)
         self.handle = h
         self.n = lib().pik_robot_num_variables(h)
+        self.n_tips = lib().pik_robot_num_tips(h)
 
     def variable(self, i: int) -> Variable:
         v = Variable()
@@ -220,6 +234,7 @@ class Solver:
     def __init__(self, robot: Robot, device: int = 0, stream: int = 0):
         self.robot = robot
         self.n = robot.n
+        self.n_tips = robot.n_tips
         h = C.c_void_p()
         rc = lib().pik_solver_create(robot.handle, device, C.c_void_p(stream) if stream else None, C.byref(h))
         if rc != PIK_OK:
@@ -234,8 +249,8 @@ class Solver:
     def solve_batch(self, params: Params, goal_pose: np.ndarray, seed: np.ndarray, first_problem_index: int = 0,
                     out: Optional[dict] = None) -> dict:
         goal_pose = np.ascontiguousarray(goal_pose, dtype=np.float64)
-        if goal_pose.ndim != 2 or goal_pose.shape[1] != 7:
-            raise ValueError("goal_pose must be [B, 7]")
+        if goal_pose.shape[1:] not in ((self.n_tips, 7),) + (((7,),) if self.n_tips == 1 else ()):
+            raise ValueError("goal_pose must be [B, n_tips, 7] ([B, 7] for one tip)")
         B = goal_pose.shape[0]
         seed = np.ascontiguousarray(seed, dtype=np.float64)
         if seed.shape == (self.n,) or seed.shape == (1, self.n):
@@ -257,12 +272,12 @@ class Solver:
         goal_pose = np.ascontiguousarray(goal_pose, dtype=np.float64)
         q = np.ascontiguousarray(q, dtype=np.float64)
         B = q.shape[0]
-        assert q.shape == (B, self.n) and goal_pose.shape == (B, 7)
+        assert q.shape == (B, self.n) and goal_pose.size == B * self.n_tips * 7
         seed = np.ascontiguousarray(seed, dtype=np.float64)
         stride = 0 if seed.shape in ((self.n,), (1, self.n)) else self.n
         cost = np.empty(B)
         sol = np.empty(B, dtype=np.int32)
-        tip = np.empty((B, 7))
+        tip = np.empty((B, 7)) if self.n_tips == 1 else np.empty((B, self.n_tips, 7))
         rc = lib().pik_eval_cost(self.handle, C.byref(params), B, _addr(goal_pose), _addr(seed), stride, _addr(q),
                                  _addr(cost), _addr(sol), _addr(tip), MEM_HOST)
         self._check(rc, "pik_eval_cost")

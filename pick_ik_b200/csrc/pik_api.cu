@@ -265,27 +265,32 @@ int pik_params_validate(const pik_params* p) {
     return PIK_OK;
 }
 
-int pik_robot_create(const pik_joint_desc* joints, int32_t n_joints, pik_robot** out) {
+int pik_robot_create_tree(const pik_joint_desc* joints, int32_t n_joints, const int32_t* parent, const int32_t* tip_joint,
+                          int32_t n_tips, const int32_t* mimic_of, const double* mimic_factor, const double* mimic_offset,
+                          pik_robot** out) {
     if (!out) return PIK_E_INVALID_ARGUMENT;
     *out = nullptr;
-    if (!joints || n_joints <= 0) return PIK_E_INVALID_ROBOT;
+    if (!joints || n_joints <= 0 || !tip_joint || n_tips <= 0) return PIK_E_INVALID_ROBOT;
+    if (mimic_of && (!mimic_factor || !mimic_offset)) return PIK_E_INVALID_ARGUMENT;
     for (int j = 0; j < n_joints; ++j) {
         const pik_joint_desc& jd = joints[j];
         if (jd.type == PIK_JOINT_FIXED) continue;
-        if (jd.type != PIK_JOINT_REVOLUTE && jd.type != PIK_JOINT_PRISMATIC) return PIK_E_INVALID_ROBOT;
-        const double a2 = jd.axis[0] * jd.axis[0] + jd.axis[1] * jd.axis[1] + jd.axis[2] * jd.axis[2];
-        if (!(std::fabs(a2 - 1.0) < 1e-6)) return PIK_E_INVALID_ROBOT;
+        if (jd.type < PIK_JOINT_FIXED || jd.type > PIK_JOINT_PLANAR) return PIK_E_INVALID_ROBOT;
+        if (jd.type == PIK_JOINT_REVOLUTE || jd.type == PIK_JOINT_PRISMATIC) {
+            const double a2 = jd.axis[0] * jd.axis[0] + jd.axis[1] * jd.axis[1] + jd.axis[2] * jd.axis[2];
+            if (!(std::fabs(a2 - 1.0) < 1e-6)) return PIK_E_INVALID_ROBOT;
+        }
         if (!(jd.min_position <= jd.max_position)) return PIK_E_INVALID_ROBOT;
     }
     pik_robot* r = new (std::nothrow) pik_robot;
     if (!r) return PIK_E_OUT_OF_MEMORY;
-    const int rc = build_dev_robot(joints, n_joints, &r->dev);
+    double rcp[kMaxVars] = {0};
+    const int rc = build_dev_robot_tree(joints, n_joints, parent, tip_joint, n_tips, mimic_of, mimic_factor, mimic_offset,
+                                        &r->dev, rcp);
     if (rc != PIK_OK) {
         delete r;
         return rc;
     }
-    double rcp[kMaxVars] = {0};
-    host_max_velocity_rcp(joints, n_joints, rcp);
     for (int i = 0; i < r->dev.n; ++i) {
         pik_variable& v = r->vars[i];
         v.min = r->dev.vmin[i];
@@ -300,6 +305,16 @@ int pik_robot_create(const pik_joint_desc* joints, int32_t n_joints, pik_robot**
     *out = r;
     return PIK_OK;
 }
+
+int pik_robot_create(const pik_joint_desc* joints, int32_t n_joints, pik_robot** out) {
+    if (!out) return PIK_E_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!joints || n_joints <= 0) return PIK_E_INVALID_ROBOT;
+    const int32_t tip = n_joints - 1;
+    return pik_robot_create_tree(joints, n_joints, nullptr, &tip, 1, nullptr, nullptr, nullptr, out);
+}
+
+int32_t pik_robot_num_tips(const pik_robot* robot) { return robot ? robot->dev.n_tips : 0; }
 
 void pik_robot_destroy(pik_robot* robot) { delete robot; }
 
@@ -318,6 +333,7 @@ const char* pik_robot_chain_signature(const pik_robot* robot) {
         case kSpecOrgIdentity: return "identity origins";
         case kSpecOrgRotX: return "x-rotation origins";
         case kSpecOrgRotY: return "y-rotation origins";
+        case kSpecTree: return "tree";
         default: return "generic";
     }
 }
@@ -535,6 +551,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
     if (!params || B < 0 || !goal_pose || !seed) return PIK_E_INVALID_ARGUMENT;
     if (!keep_on_device && (!solution || !error_code)) return PIK_E_INVALID_ARGUMENT;
     const int n = s->robot.dev.n;
+    const int T = s->robot.dev.n_tips;
     if (seed_stride != 0 && seed_stride != n) return PIK_E_INVALID_ARGUMENT;
     if (memory != PIK_MEM_HOST && memory != PIK_MEM_DEVICE) return PIK_E_INVALID_ARGUMENT;
     if (B > (int64_t)1 << 30 || first_problem_index < 0 || first_problem_index + B > (int64_t)0xffffffffll)
@@ -571,7 +588,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
     sb.stop_on_first = params->memetic_stop_on_first_solution ? 1 : 0;
     make_round_keys(params->rng_seed, sb.round_key);
     if (memory == PIK_MEM_HOST) {
-        if ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8))) return rc;
+        if ((rc = ensure(s, s->d_goal, (size_t)B * 7 * T * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8))) return rc;
         sb.goal_pose = static_cast<double*>(s->d_goal.ptr);
         sb.seed = static_cast<double*>(s->d_seed.ptr);
     } else {
@@ -631,7 +648,10 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
         sb.counters = static_cast<int32_t*>(s->d_counters.ptr);
         sb.sched = static_cast<int32_t*>(s->d_sched.ptr);
         // one plan, sized for the largest sub-batch, serves every sub-batch
-        plan = plan_generations(n, P, pr.E, slice_problems * S, s->sm_count, wide_warps_per_sm(), !trace_each_generation());
+        // (species that may be terminated by one another advance one generation per launch: no persistent launch)
+        const bool lockstep_species = S > 1 && params->memetic_stop_on_first_solution;
+        plan = plan_generations(n, T, P, pr.E, slice_problems * S, s->sm_count, wide_warps_per_sm(),
+                                !trace_each_generation() && !lockstep_species);
         pr.sm_count = s->sm_count;
         pr.lanes_max = plan.lanes_max;
         pr.wide_capacity_lanes = plan.wide_capacity_lanes;
@@ -649,7 +669,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
         const size_t F = 2 * (size_t)n + 2;
         w.B = pk * S;
         w.first_problem_index = first_problem_index + p0;
-        w.goal_pose = sb.goal_pose + 7 * (size_t)p0;
+        w.goal_pose = sb.goal_pose + 7 * (size_t)T * (size_t)p0;
         w.seed = sb.seed + (size_t)seed_stride * (size_t)p0;
         w.solution = sb.solution + (size_t)s0 * n;
         w.error_code = sb.error_code + s0;
@@ -676,12 +696,12 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
     auto issue = [&]() -> int {
         PIK_CUDA(s, cudaEventRecord(s->ev0, st));
         if (memory == PIK_MEM_HOST) {
-            PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
+            PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * T * 8, cudaMemcpyHostToDevice, st));
             PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
         }
         PIK_CUDA(s, cudaMemsetAsync(sb.stats, 0, (size_t)K * 8 * sizeof(unsigned long long), st));
         if (!global) {
-            PIK_CUDA(s, launch_gd_local(st, s->spec, n, sb, s->sm_count));
+            PIK_CUDA(s, launch_gd_local(st, s->spec, n, T, sb, s->sm_count));
             s->stats.kernel_launches += 1;
         } else {
             PIK_CUDA(s, cudaMemsetAsync(sb.counters, 0, (size_t)K * n_counters * sizeof(int32_t), st));
@@ -696,7 +716,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
                     sk = s->sub_streams[k];
                     PIK_CUDA(s, cudaStreamWaitEvent(sk, s->ev2, 0));  // inputs and cleared counters are in place
                 }
-                PIK_CUDA(s, launch_memetic_init(sk, s->spec, n, P, pr.E, w));
+                PIK_CUDA(s, launch_memetic_init(sk, s->spec, n, T, P, pr.E, w));
                 s->stats.kernel_launches += 1;
                 if (K == 1) PIK_CUDA(s, cudaEventRecord(s->ev2, st));
                 const int n_gens = plan.first_launch_runs_all ? 1 : pr.max_generations;
@@ -805,6 +825,7 @@ int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const doub
     s->last_error.clear();
     if (!params || B < 0 || !goal_pose || !seed || !q) return PIK_E_INVALID_ARGUMENT;
     const int n = s->robot.dev.n;
+    const int T = s->robot.dev.n_tips;
     if (seed_stride != 0 && seed_stride != n) return PIK_E_INVALID_ARGUMENT;
     if (memory != PIK_MEM_HOST && memory != PIK_MEM_DEVICE) return PIK_E_INVALID_ARGUMENT;
     int rc = pik_params_validate(params);
@@ -815,9 +836,9 @@ int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const doub
     cudaStream_t st = s->stream;
     const size_t seed_elems = seed_stride ? (size_t)B * n : (size_t)n;
     if (memory == PIK_MEM_HOST &&
-        ((rc = ensure(s, s->d_goal, (size_t)B * 7 * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8)) ||
+        ((rc = ensure(s, s->d_goal, (size_t)B * 7 * T * 8)) || (rc = ensure(s, s->d_seed, seed_elems * 8)) ||
          (rc = ensure(s, s->d_q, (size_t)B * n * 8)) || (rc = ensure(s, s->d_cost, (size_t)B * 8)) ||
-         (rc = ensure(s, s->d_issol, (size_t)B * 4)) || (rc = ensure(s, s->d_tip, (size_t)B * 7 * 8))))
+         (rc = ensure(s, s->d_issol, (size_t)B * 4)) || (rc = ensure(s, s->d_tip, (size_t)B * 7 * T * 8))))
         return rc;
     if ((rc = constants_acquire(s, s->robot.dev, pr)) != PIK_OK) return rc;
     auto issue = [&]() -> int {
@@ -825,7 +846,7 @@ int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const doub
             PIK_CUDA(s, launch_eval_cost(st, n, B, goal_pose, seed, seed_stride, q, cost, is_solution, tip_pose));
             return PIK_OK;
         }
-        PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
+        PIK_CUDA(s, cudaMemcpyAsync(s->d_goal.ptr, goal_pose, (size_t)B * 7 * T * 8, cudaMemcpyHostToDevice, st));
         PIK_CUDA(s, cudaMemcpyAsync(s->d_seed.ptr, seed, seed_elems * 8, cudaMemcpyHostToDevice, st));
         PIK_CUDA(s, cudaMemcpyAsync(s->d_q.ptr, q, (size_t)B * n * 8, cudaMemcpyHostToDevice, st));
         PIK_CUDA(s, launch_eval_cost(st, n, B, static_cast<double*>(s->d_goal.ptr),
@@ -835,7 +856,7 @@ int pik_eval_cost(pik_solver* s, const pik_params* params, int64_t B, const doub
                                      tip_pose ? static_cast<double*>(s->d_tip.ptr) : nullptr));
         if (cost) PIK_CUDA(s, cudaMemcpyAsync(cost, s->d_cost.ptr, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
         if (is_solution) PIK_CUDA(s, cudaMemcpyAsync(is_solution, s->d_issol.ptr, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-        if (tip_pose) PIK_CUDA(s, cudaMemcpyAsync(tip_pose, s->d_tip.ptr, (size_t)B * 7 * 8, cudaMemcpyDeviceToHost, st));
+        if (tip_pose) PIK_CUDA(s, cudaMemcpyAsync(tip_pose, s->d_tip.ptr, (size_t)B * 7 * T * 8, cudaMemcpyDeviceToHost, st));
         return PIK_OK;
     };
     rc = issue();

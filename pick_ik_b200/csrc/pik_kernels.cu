@@ -70,13 +70,13 @@ __host__ __device__ inline int pow2_at_least(int v) {
     return p;
 }
 
-__host__ __device__ inline size_t warp_smem_bytes(int n, int P, int PW) {
-    size_t d = (size_t)5 * n * kS + (fit_in_sc(n, P) ? 0 : (size_t)P) + (size_t)PW * 7 + 3 * 32;
+__host__ __device__ inline size_t warp_smem_bytes(int n, int P, int PW, int T) {
+    size_t d = (size_t)5 * n * kS + (fit_in_sc(n, P) ? 0 : (size_t)P) + (size_t)PW * 7 * T + 3 * 32;
     size_t i = 32 + 33 + 32 + 32 + 4;
     return ((d * 8 + i * 4 + (size_t)pow2_at_least(P) * 2) + 15) & ~size_t(15);
 }
 
-__device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P, int PW) {
+__device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P, int PW, int T) {
     WarpSmem W;
     double* d = reinterpret_cast<double*>(base);
     W.q = d; d += (size_t)n * kS;
@@ -89,7 +89,7 @@ __device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P
     } else {
         W.fit = d; d += P;
     }
-    W.goal = d; d += PW * 7;
+    W.goal = d; d += PW * 7 * T;  // [PW][T][7]: the goal frame of every tip
     W.efit = d; d += 32;
     W.eext = d; d += 32;
     W.f0s = d; d += 32;
@@ -142,10 +142,18 @@ __global__ void __launch_bounds__(kThreads) eval_cost_kernel(int64_t B, const do
     double* col = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (n + 7) * kS + lane;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    double g7[7];
-    goal_from_pose(goal_pose + 7 * b, g7);
+    const int T = c_rb.n_tips;
+    double g7[7 * kMaxTips];
+    goals_from_poses(goal_pose + (size_t)(7 * T) * (size_t)b, g7);
     const double* sd = seed + b * seed_stride;
     for (int j = 0; j < n; ++j) col[j * kS] = q[b * n + j];
+    double aux[5];
+    if (c_rb.is_tree) {
+        const double c = eval_tree(col, nullptr, kViewPlain, -1, 0.0, g7, sd, aux, tip_pose ? tip_pose + (size_t)(7 * T) * (size_t)b : nullptr);
+        if (cost) cost[b] = c;
+        if (is_solution) is_solution[b] = solution_from_aux(aux) ? 1 : 0;
+        return;
+    }
     // tip frame: walk here (the tip pose is an output of this kernel only)
     const ConfigView cv{col, nullptr, kViewPlain, -1, 0.0};
     Frame F;
@@ -157,7 +165,6 @@ __global__ void __launch_bounds__(kThreads) eval_cost_kernel(int64_t B, const do
         walk_joint<GenericSpec>(F, j, j > 0, cv.at(j), sj, cj);
     }
     if (c_rb.has_tip) frame_mul_const(F, c_rb.tip_R, c_rb.tip_t);
-    double aux[5];
     const double c = total_cost(g7, F, cv, sd, aux);
     if (cost) cost[b] = c;
     if (is_solution) is_solution[b] = solution_from_aux(aux) ? 1 : 0;
@@ -179,10 +186,11 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (5 * n + 12 + 7) * kS;
+    const int T = c_rb.n_tips;
+    double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (5 * n + 12 + 7 * T) * kS;
     GdState st{base + lane, base + (size_t)n * kS + lane, base + (size_t)2 * n * kS + lane,
                base + (size_t)3 * n * kS + lane, base + (size_t)5 * n * kS + lane, 0.0, 0.0};
-    double* g7 = base + (size_t)(5 * n + 12) * kS + lane * 7;  // 7 contiguous doubles per lane
+    double* g7 = base + (size_t)(5 * n + 12) * kS + lane * 7 * T;  // 7 contiguous doubles per lane and tip
     unsigned long long* next_problem = reinterpret_cast<unsigned long long*>(sb.stats + 5);
     int64_t b = -1;
     const double* sd = nullptr;
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(kThreads) gd_local_kernel(const __grid_constan
                         st.best[j * kS] = sd[j];
                         st.g[j * kS] = 0.0;
                     }
-                    goal_from_pose(sb.goal_pose + 7 * b, g7);
+                    goals_from_poses(sb.goal_pose + (size_t)(7 * c_rb.n_tips) * (size_t)b, g7);
                     const double c0 = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, aux);
                     if (c_pr.stop_on_valid && solution_from_aux(aux)) {  // ik_gradient.cpp:102-104
                         write_result(sb, n, b, true, st.best, kS, sd, c0, 0);
@@ -302,7 +310,7 @@ __device__ __forceinline__ void init_population_warp(const SolveBuffers& sb, con
             const Stream st = make_stream((uint32_t)(sb.first_problem_index + problem_of(sb, b)), kStreamInit,
                                           (uint32_t)m.init_epoch, (uint32_t)e, species_of(sb, b));
             random_valid_configuration(sb, st, col);
-            f = eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k_e,
+            f = eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + (7 * c_rb.n_tips) * k_e,
                            sb.seed + problem_of(sb, b) * sb.seed_stride, nullptr);
         }
         W.efit[lane] = f;
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = c_rb.n, P = c_pr.P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, PW), n, P, PW);
+    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, PW, c_rb.n_tips), n, P, PW, c_rb.n_tips);
     const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * PW;
     if (base >= sb.B) return;
     bool keep = false;
@@ -356,8 +364,8 @@ __global__ void __launch_bounds__(kThreads) memetic_init_kernel(const __grid_con
         if (b < sb.B) {
             const int pb = problem_of(sb, b);
             const double* sd = sb.seed + pb * sb.seed_stride;
-            double* g7 = W.goal + 7 * lane;
-            goal_from_pose(sb.goal_pose + 7 * (size_t)pb, g7);
+            double* g7 = W.goal + (7 * c_rb.n_tips) * lane;
+            goals_from_poses(sb.goal_pose + (size_t)(7 * c_rb.n_tips) * (size_t)pb, g7);
             double* col = W.q + lane;
             double* hdr = sb.hdr + (size_t)b * (n + 2);
             for (int j = 0; j < n; ++j) {
@@ -414,8 +422,8 @@ __device__ __forceinline__ void finish_terminated(const SolveBuffers& sb, const 
     const double* hdr = sb.hdr + (size_t)b * (n + 2);
     bool found = false;
     if (!c_pr.stop_on_valid) {
-        double* g7 = W.goal + 7 * lane;
-        goal_from_pose(sb.goal_pose + 7 * (size_t)pb, g7);
+        double* g7 = W.goal + (7 * c_rb.n_tips) * lane;
+        goals_from_poses(sb.goal_pose + (size_t)(7 * c_rb.n_tips) * (size_t)pb, g7);
         double* col = W.q + lane;
         for (int j = 0; j < n; ++j) col[j * kS] = hdr[j];
         double aux[5];
@@ -633,14 +641,14 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     const int chunk = S::kWide ? wpb : 1;
     const int n_chunks = (units + chunk - 1) / chunk;
     const int rot = sb.sm_rotation % nsm;
-    const bool persistent = S::kWide && PW == 1 && units <= c_pr.persistent_units_max && !(sb.group_term && sb.stop_on_first);
+    const bool persistent = S::kWide && PW == 1 && units <= c_pr.persistent_units_max;  // (0 for species in lockstep)
     const int max_gens = persistent ? c_pr.max_generations - gen : 1;
     // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
     // GD step (below): warps that run the same code at the same time share their instruction-cache fills.
     const bool lockstep = L == 1 && (c_pr.lockstep & 1) != 0;
     const bool lockstep_rep = L == 1 && (c_pr.lockstep & 2) != 0;
     const int pw_carve = S::kWide ? wide_problems_per_warp_max(E) : PW;
-    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, pw_carve), n, P, pw_carve);
+    const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, pw_carve, c_rb.n_tips), n, P, pw_carve, c_rb.n_tips);
     const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;
     int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
     bool worked = false, sweeping = false;
@@ -732,7 +740,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         }
         W.pidx[lane] = b;
         W.flag[lane] = 0;
-        if (b >= 0) goal_from_pose(sb.goal_pose + 7 * (size_t)problem_of(sb, b), W.goal + 7 * lane);
+        if (b >= 0) goals_from_poses(sb.goal_pose + (size_t)(7 * c_rb.n_tips) * (size_t)problem_of(sb, b), W.goal + (7 * c_rb.n_tips) * lane);
     }
     __syncwarp();
 
@@ -775,7 +783,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         double best_cost = 0.0;
         if (L == 1) {
             GdState st{W.q + c, W.g + c, W.best + c, W.sc + c, nullptr, 0.0, 0.0};
-            const double* g7 = W.goal + 7 * (valid ? k : 0);
+            const double* g7 = W.goal + (7 * c_rb.n_tips) * (valid ? k : 0);
             if (valid) st.local_cost = st.best_cost = eval_chain<S>(st.q, nullptr, kViewPlain, -1, 0.0, nullptr, st.sc, g7, sd, nullptr);
             bool going = valid;
             double previous_cost = 0.0;
@@ -796,12 +804,12 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         } else {
 #ifdef PIK_PHASE_TRACE
             long long ph[5] = {0, 0, 0, 0, 0};
-            const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + 7 * (valid ? k : 0), sd, best_cost, dbg ? ph : nullptr);
+            const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + (7 * c_rb.n_tips) * (valid ? k : 0), sd, best_cost, dbg ? ph : nullptr);
             if (dbg)
                 printf("pik wide gd phases: sincos %lld  roundA %lld  control %lld  roundB %lld  accept %lld\n", ph[0], ph[1],
                        ph[2], ph[3], ph[4]);
 #else
-            const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + 7 * (valid ? k : 0), sd, best_cost);
+            const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + (7 * c_rb.n_tips) * (valid ? k : 0), sd, best_cost);
 #endif
             if (leader) gd_steps = steps;
         }
@@ -836,7 +844,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         const uint16_t* ord_in = order_ptr(sb, iter & 1, b, P);
         uint16_t* ord_out = order_ptr(sb, (iter & 1) ^ 1, b, P);
         const double* sd = sb.seed + (size_t)problem_of(sb, b) * sb.seed_stride;
-        const double* g7 = W.goal + 7 * k;
+        const double* g7 = W.goal + (7 * c_rb.n_tips) * k;
         const int c0 = k * E;  // first elite column of this problem
         const uint32_t rng_problem = (uint32_t)(sb.first_problem_index + problem_of(sb, b));
         const uint32_t rng_species = species_of(sb, b);
@@ -1064,7 +1072,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                 double* col = W.q + lane;
                 for (int j = 0; j < n; ++j) col[j * kS] = hdr[j];
                 double aux[5];
-                eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + 7 * k, sd, aux);
+                eval_chain<S>(col, nullptr, kViewPlain, -1, 0.0, nullptr, nullptr, W.goal + (7 * c_rb.n_tips) * k, sd, aux);
                 s = solution_from_aux(aux);
             }
             bool done = false, found = false;
@@ -1235,7 +1243,7 @@ int memetic_max_lanes_per_elite(int E) {
     return L < 1 ? 1 : L;
 }
 
-MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
+MemeticShape memetic_shape(int n, int T, int P, int E, int lanes_per_elite) {
     MemeticShape s;
     int L = lanes_per_elite < 1 ? 1 : lanes_per_elite;
     if (L > memetic_max_lanes_per_elite(E)) L = memetic_max_lanes_per_elite(E);
@@ -1245,16 +1253,16 @@ MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite) {
     // the wide flavour carves its shared memory for the largest number of problems per warp it may be given
     const int pw_carve = L == 1 ? s.problems_per_warp : wide_problems_per_warp_max(E);
     // a large population may not leave room for 8 warps' worth of shared memory
-    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, pw_carve) > 112 * 1024) --s.warps;
+    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, pw_carve, T) > 112 * 1024) --s.warps;
     s.threads = 32 * s.warps;
-    s.smem = s.warps * warp_smem_bytes(n, P, pw_carve);
+    s.smem = s.warps * warp_smem_bytes(n, P, pw_carve, T);
     return s;
 }
 
-GenerationPlan plan_generations(int n, int P, int E, int64_t n_sub, int sm_count, long long wide_warps_per_sm,
+GenerationPlan plan_generations(int n, int T, int P, int E, int64_t n_sub, int sm_count, long long wide_warps_per_sm,
                                 bool allow_persistent) {
     GenerationPlan g;
-    const MemeticShape t = memetic_shape(n, P, E, 1);
+    const MemeticShape t = memetic_shape(n, T, P, E, 1);
     g.threads_t = t.threads;
     g.smem_t = t.smem;
     // grids of resident CTAs (2 per SM for the throughput flavour, 3 for the wide one): the CTAs claim their work from
@@ -1267,7 +1275,7 @@ GenerationPlan plan_generations(int n, int P, int E, int64_t n_sub, int sm_count
     // largest power of two the doubling of lanes_for can reach
     int lw = 1;
     while (lw * 2 <= g.lanes_max) lw *= 2;
-    const MemeticShape w = memetic_shape(n, P, E, lw);
+    const MemeticShape w = memetic_shape(n, T, P, E, lw);
     g.threads_w = w.threads;
     g.smem_w = w.smem;
     const int64_t units_w = (n_sub + w.problems_per_warp - 1) / w.problems_per_warp;
@@ -1287,7 +1295,7 @@ GenerationPlan plan_generations(int n, int P, int E, int64_t n_sub, int sm_count
     return g;
 }
 
-size_t gd_local_smem_bytes(int n) { return (size_t)kWarpsPerBlock * (5 * n + 12 + 7) * kS * sizeof(double); }
+size_t gd_local_smem_bytes(int n, int T) { return (size_t)kWarpsPerBlock * (5 * n + 12 + 7 * T) * kS * sizeof(double); }
 
 // Compiled chain signatures (see StaticSpec).  kinds nibble: X 0, Y 1, Z 2, general 3, prismatic 4.
 // Every signature is compiled in two flavours: throughput (generation launches with one lane per elite,
@@ -1306,6 +1314,7 @@ static bool origins_have_pattern(const DevRobot& rb, int origin_cls, int tip_cls
 }
 
 int select_spec(const DevRobot& rb) {
+    if (rb.is_tree) return kSpecTree;
     // PIK_GENERIC_ONLY: the generic kernels; PIK_NO_STATIC: no compile-time n / kinds (pattern kernels only)
     if (std::getenv("PIK_GENERIC_ONLY")) return kSpecGeneric;
     unsigned long long kinds = 0;
@@ -1336,6 +1345,8 @@ int select_spec(const DevRobot& rb) {
         case kSpecOrgRotY * 2: { using S = PatternSpec<kOrgRotY, kOrgGeneral, false>; CALL; break; }    \
         case kSpecOrgRotY * 2 + 1: { using S = PatternSpec<kOrgRotY, kOrgGeneral, true>; CALL; break; } \
         case kSpecGeneric * 2 + 1: { using S = GenericSpecW; CALL; break; }                            \
+        case kSpecTree * 2: { using S = TreeSpec<false>; CALL; break; }                                \
+        case kSpecTree * 2 + 1: { using S = TreeSpec<true>; CALL; break; }                             \
         default: { using S = GenericSpec; CALL; break; }                                               \
     }
 
@@ -1373,22 +1384,22 @@ cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double
     return cudaGetLastError();
 }
 
-cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb, int sm_count) {
+cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, int T, const SolveBuffers& sb, int sm_count) {
     if (sb.B <= 0) return cudaSuccess;
     // resident CTAs only (3 per SM at 168 registers): the lanes pull their problems from a counter
     int64_t blocks64 = (sb.B + kThreads - 1) / kThreads;
     if (blocks64 > (int64_t)3 * sm_count) blocks64 = (int64_t)3 * sm_count;
     const unsigned blocks = (unsigned)blocks64;
-    PIK_DISPATCH_SPEC(spec, false, (gd_local_kernel<S><<<blocks, kThreads, gd_local_smem_bytes(n), stream>>>(sb)));
+    PIK_DISPATCH_SPEC(spec, false, (gd_local_kernel<S><<<blocks, kThreads, gd_local_smem_bytes(n, T), stream>>>(sb)));
     return cudaGetLastError();
 }
 
-cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb) {
+cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int T, int P, int E, const SolveBuffers& sb) {
     if (sb.B <= 0) return cudaSuccess;
-    MemeticShape s = memetic_shape(n, P, E, 1);
+    MemeticShape s = memetic_shape(n, T, P, E, 1);
     s.warps = kWarpsPerBlock;
     s.threads = kThreads;
-    s.smem = s.warps * warp_smem_bytes(n, P, s.problems_per_warp);
+    s.smem = s.warps * warp_smem_bytes(n, P, s.problems_per_warp, T);
     const int64_t per_block = (int64_t)s.problems_per_warp * s.warps;
     const unsigned blocks = (unsigned)((sb.B + per_block - 1) / per_block);
     PIK_DISPATCH_SPEC(spec, false, (memetic_init_kernel<S><<<blocks, s.threads, s.smem, stream>>>(sb, s.problems_per_warp)));

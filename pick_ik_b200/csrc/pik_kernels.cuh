@@ -18,9 +18,9 @@ struct MemeticShape {
     int problems_per_warp;  // PW = 32 / (E * L)
     size_t smem;            // per CTA
 };
-MemeticShape memetic_shape(int n, int P, int E, int lanes_per_elite);
+MemeticShape memetic_shape(int n, int n_tips, int P, int E, int lanes_per_elite);
 int memetic_max_lanes_per_elite(int E);
-size_t gd_local_smem_bytes(int n);
+size_t gd_local_smem_bytes(int n, int n_tips);
 
 // Copies the robot table and the solver parameters to constant memory (ordered on `stream`).
 cudaError_t upload_constants(cudaStream_t stream, const DevRobot& robot, const DevParams& pr);
@@ -34,11 +34,12 @@ cudaError_t launch_eval_cost(cudaStream_t stream, int n, int64_t B, const double
 // joint origin (from the second joint on) has the named sparsity pattern (OriginClass) -- identity (URDFs whose
 // origins only translate: Fetch), rotation about x, rotation about y (the UR family) -- so the chain walk
 // skips the terms that are exact zeros.  kSpecGeneric: anything.
-enum : int { kSpecGeneric = 0, kSpecAllZ7 = 1, kSpecOrgIdentity = 2, kSpecOrgRotX = 3, kSpecOrgRotY = 4, kSpecCount = 5 };
+// kSpecTree: kinematic trees, several tips, floating / planar / mimic joints (DevRobot::is_tree).
+enum : int { kSpecGeneric = 0, kSpecAllZ7 = 1, kSpecOrgIdentity = 2, kSpecOrgRotX = 3, kSpecOrgRotY = 4, kSpecTree = 5, kSpecCount = 6 };
 int select_spec(const DevRobot& robot);
 
-cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, const SolveBuffers& sb, int sm_count);
-cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int P, int E, const SolveBuffers& sb);
+cudaError_t launch_gd_local(cudaStream_t stream, int spec, int n, int n_tips, const SolveBuffers& sb, int sm_count);
+cudaError_t launch_memetic_init(cudaStream_t stream, int spec, int n, int n_tips, int P, int E, const SolveBuffers& sb);
 // The launches of a global-mode solve over n_sub sub-problems, planned once per call (nothing is read back from the
 // device while the solve runs).  Per generation: one launch of the throughput flavour (blocks_t) and one of the
 // wide flavour (blocks_w); each reads the size of the generation's active list and returns at once unless the lane
@@ -53,7 +54,7 @@ struct GenerationPlan {
     long long wide_capacity_lanes;
     bool use_throughput, use_wide, first_launch_runs_all;
 };
-GenerationPlan plan_generations(int n, int P, int E, int64_t n_sub, int sm_count, long long wide_warps_per_sm,
+GenerationPlan plan_generations(int n, int n_tips, int P, int E, int64_t n_sub, int sm_count, long long wide_warps_per_sm,
                                 bool allow_persistent);
 cudaError_t launch_memetic_generation(cudaStream_t stream, int spec, const GenerationPlan& plan, const SolveBuffers& sb,
                                       int gen, bool wide);

@@ -5,14 +5,19 @@
 
 namespace pik {
 
-constexpr int kMaxVars = 16;
+constexpr int kMaxVars = 16;          // variables, and moving joints (steps)
+constexpr int kMaxTips = 4;
+constexpr int kMaxSavedFrames = 4;    // frames of branch points kept while a tree is walked
 constexpr int kMaxElites = 32;       // the elites of one problem live in one warp
 constexpr int kMaxPopulation = 1024;
 constexpr int kSmDenseSize = 256;    // %smid values are below this (a power of two)
 
 // kPrisX/Y/Z: prismatic along +-x / y / z (sign in DevRobot::sign): t += column * (sign * q), which is what the general
 // form computes up to the sign of exact zeros (fma(x, +-0, t) == t)
-enum StepKind : int { kRevX = 0, kRevY = 1, kRevZ = 2, kRevGeneral = 3, kPrismatic = 4, kPrisX = 5, kPrisY = 6, kPrisZ = 7 };
+// kFloating (7 variables: x y z, quaternion x y z w) and kPlanar (x y theta): src/forward_kinematics.cpp:64-79; tree
+// kernels only
+enum StepKind : int { kRevX = 0, kRevY = 1, kRevZ = 2, kRevGeneral = 3, kPrismatic = 4, kPrisX = 5, kPrisY = 6, kPrisZ = 7,
+                      kFloating = 8, kPlanar = 9 };
 
 // Sparsity pattern of a constant rotation (URDF origins are mostly rotations about one coordinate axis, often
 // by multiples of pi/2): entries that are exactly 0 or 1 need no arithmetic -- x * 1 == x and fma(x, 0, y) == y
@@ -41,6 +46,23 @@ struct DevRobot {
     double tip_R[9];
     double tip_t[3];
     double vmin[kMaxVars], vmax[kMaxVars], vmid[kMaxVars], vhalf[kMaxVars], vfac[kMaxVars];
+    // ---- kinematic trees, several tips, multi-variable and mimic joints (is_tree: served by the tree kernels only).
+    // Step k (a moving joint, parents before children): frame = frame of step parent[k] (-1: the model root) * folded
+    // origin R[k], t[k] * joint motion on variables var0[k].. (value * mimic_factor + mimic_offset for a mimic joint).
+    // A serial single-tip chain of one-variable joints has parent[k] = k - 1, var0[k] = k and its tip in R[n], t[n].
+    int is_tree;
+    int n_steps;
+    int n_tips;
+    int pad2_;
+    int parent[kMaxVars];
+    int var0[kMaxVars];
+    int load_slot[kMaxVars];  // where the walk finds the parent frame: -1 the previous step, -2 the model root, >= 0 a saved frame
+    int save_slot[kMaxVars];  // >= 0: the frame of this step is kept in that slot for a later branch
+    double mimic_factor[kMaxVars], mimic_offset[kMaxVars];
+    int tip_step[kMaxTips];   // step the tip link hangs on (-1: the model root)
+    int tip_has[kMaxTips];    // fixed transform between that step and the tip link
+    double tips_R[kMaxTips][9];
+    double tips_t[kMaxTips][3];
 };
 
 // Solver parameters as the kernels see them (pick_ik_plugin.cpp:97-129,166-196 applied).

@@ -22,6 +22,8 @@ import numpy as np
 JOINT_FIXED = 0
 JOINT_REVOLUTE = 1
 JOINT_PRISMATIC = 2
+JOINT_FLOATING = 3  # 7 variables: x y z, quaternion x y z w (/root/reference/src/forward_kinematics.cpp:64-70)
+JOINT_PLANAR = 4    # 3 variables: x y theta (forward_kinematics.cpp:71-79)
 
 # numpy mirror of pik_joint_desc / orc_joint_desc (natural C alignment, 176 bytes)
 JOINT_DESC_DTYPE = np.dtype(
@@ -77,6 +79,12 @@ class Joint:
     upper: float = 0.0
     velocity: float = 0.0
     continuous: bool = False  # URDF "continuous": position_bounded_ = false, bounds -pi..pi
+    # kinematic trees (RobotTree): index of the joint whose child link this joint hangs on (-1: the model root)
+    parent: int = -1
+    # mimic joints: index of the joint followed, value = mimic_factor * master + mimic_offset
+    mimic_of: int = -1
+    mimic_factor: float = 1.0
+    mimic_offset: float = 0.0
 
 
 @dataclass
@@ -95,27 +103,63 @@ class RobotChain:
         return len(self.variable_names)
 
     def joint_desc(self) -> np.ndarray:
-        out = np.zeros(len(self.joints), dtype=JOINT_DESC_DTYPE)
-        for i, j in enumerate(self.joints):
-            out[i]["type"] = j.type
-            out[i]["origin_R"] = rpy_to_matrix(*j.rpy).reshape(9)
-            out[i]["origin_t"] = np.asarray(j.xyz, dtype=np.float64)
-            ax = np.asarray(j.axis, dtype=np.float64)
-            if j.type != JOINT_FIXED:
-                ax = ax / math.sqrt(float(ax @ ax))  # RevoluteJointModel::setAxis normalises
-            out[i]["axis"] = ax
-            if j.type == JOINT_FIXED:
-                continue
-            if j.continuous:
-                out[i]["bounded"] = 0
-                out[i]["min_position"] = -math.pi
-                out[i]["max_position"] = math.pi
-            else:
-                out[i]["bounded"] = 1
-                out[i]["min_position"] = j.lower
-                out[i]["max_position"] = j.upper
-            out[i]["max_velocity"] = abs(j.velocity)
-        return out
+        return joints_to_desc(self.joints)
+
+
+def joints_to_desc(joints: Sequence[Joint]) -> np.ndarray:
+    out = np.zeros(len(joints), dtype=JOINT_DESC_DTYPE)
+    for i, j in enumerate(joints):
+        out[i]["type"] = j.type
+        out[i]["origin_R"] = rpy_to_matrix(*j.rpy).reshape(9)
+        out[i]["origin_t"] = np.asarray(j.xyz, dtype=np.float64)
+        ax = np.asarray(j.axis, dtype=np.float64)
+        if j.type in (JOINT_REVOLUTE, JOINT_PRISMATIC):
+            ax = ax / math.sqrt(float(ax @ ax))  # RevoluteJointModel::setAxis normalises
+        out[i]["axis"] = ax
+        if j.type == JOINT_FIXED:
+            continue
+        if j.continuous:
+            out[i]["bounded"] = 0
+            out[i]["min_position"] = -math.pi
+            out[i]["max_position"] = math.pi
+        else:
+            out[i]["bounded"] = 1
+            out[i]["min_position"] = j.lower
+            out[i]["max_position"] = j.upper
+        out[i]["max_velocity"] = abs(j.velocity)
+    return out
+
+
+VARIABLES_OF = {JOINT_FIXED: 0, JOINT_REVOLUTE: 1, JOINT_PRISMATIC: 1, JOINT_FLOATING: 7, JOINT_PLANAR: 3}
+
+
+@dataclass
+class RobotTree:
+    """A kinematic tree with several tip links (one goal pose per tip, /root/reference/src/goal.cpp:80-89,163-175),
+    floating / planar joints and mimic joints: the arguments of pik_robot_create_tree / orc_robot_build_tree.
+    Joints are listed parents first; Joint.parent is the index of the joint above (-1: the model root)."""
+    name: str
+    joints: List[Joint] = field(default_factory=list)
+    tip_joints: List[int] = field(default_factory=list)
+
+    @property
+    def num_variables(self) -> int:
+        return sum(VARIABLES_OF[j.type] for j in self.joints if j.mimic_of < 0)
+
+    @property
+    def num_tips(self) -> int:
+        return len(self.tip_joints)
+
+    def joint_desc(self) -> np.ndarray:
+        return joints_to_desc(self.joints)
+
+    def tree_arrays(self):
+        parent = np.array([j.parent for j in self.joints], dtype=np.int32)
+        tips = np.array(self.tip_joints, dtype=np.int32)
+        mimic_of = np.array([j.mimic_of for j in self.joints], dtype=np.int32)
+        factor = np.array([j.mimic_factor for j in self.joints], dtype=np.float64)
+        offset = np.array([j.mimic_offset for j in self.joints], dtype=np.float64)
+        return self.joint_desc(), parent, tips, mimic_of, factor, offset
 
 
 def to_urdf(chain: RobotChain) -> str:
@@ -278,5 +322,84 @@ def single(kind: str = "revolute") -> RobotChain:
 def single_prismatic() -> RobotChain:
     return single("prismatic")
 
+
+def two_arm() -> RobotTree:
+    """Two 3-joint arms on a common revolute torso, one tool tip each (a fixed joint between the torso and the
+    branch point, fixed tool frames): the smallest tree with a shared chain prefix and two goal poses."""
+    R, F = JOINT_REVOLUTE, JOINT_FIXED
+    j = [
+        Joint("torso", R, (0, 0, 0.4), (0, 0, 0), (0, 0, 1), -1.5, 1.5, 1.0, parent=-1),
+        Joint("chest", F, (0, 0, 0.3), (0.1, 0, 0), parent=0),
+        Joint("l_shoulder", R, (0, 0.2, 0), (0, 0, 0.3), (0, 1, 0), -2.0, 2.0, 1.5, parent=1),
+        Joint("l_elbow", R, (0.3, 0, 0), (0, 0, 0), (0, 1, 0), -2.2, 2.2, 1.5, parent=2),
+        Joint("l_wrist", R, (0.25, 0, 0), (0, 0, 0), (1, 0, 0), velocity=2.0, continuous=True, parent=3),
+        Joint("l_tool", F, (0.1, 0, 0), (0, 0.2, 0), parent=4),
+        Joint("r_shoulder", R, (0, -0.2, 0), (0, 0, -0.3), (0, 1, 0), -2.0, 2.0, 1.5, parent=1),
+        Joint("r_elbow", R, (0.3, 0, 0), (0, 0, 0), (0, 1, 0), -2.2, 2.2, 1.5, parent=6),
+        Joint("r_wrist", R, (0.25, 0, 0), (0, 0, 0), (0.6, 0, 0.8), -2.5, 2.5, 2.0, parent=7),
+        Joint("r_tool", F, (0.1, 0, 0), (0, -0.2, 0), parent=8),
+    ]
+    return RobotTree("two_arm", j, [5, 9])
+
+
+def three_tip() -> RobotTree:
+    """Three tips: two branches straight off the model root, a tip on an intermediate link (a moving joint's own
+    child link, no tool frame) and a prismatic joint."""
+    R, F, P = JOINT_REVOLUTE, JOINT_FIXED, JOINT_PRISMATIC
+    j = [
+        Joint("a0", R, (0.1, 0, 0), (0, 0, 0), (0, 0, 1), -2.0, 2.0, 1.0, parent=-1),
+        Joint("a1", R, (0.3, 0, 0), (0.2, 0, 0), (0, 1, 0), -1.8, 1.8, 1.0, parent=0),   # tip 0: a1's child link
+        Joint("a2", P, (0.2, 0, 0), (0, 0, 0), (1, 0, 0), -0.1, 0.3, 0.4, parent=1),
+        Joint("a_tool", F, (0.05, 0, 0.02), (0, 0, 0.1), parent=2),                        # tip 1
+        Joint("base_b", F, (-0.2, 0.1, 0), (0, 0, 1.0), parent=-1),
+        Joint("b0", R, (0, 0, 0.2), (0, 0, 0), (0, 0, 1), -3.0, 3.0, 2.0, parent=4),
+        Joint("b1", R, (0.25, 0, 0), (0, 0.3, 0), (0, -1, 0), -1.5, 1.5, 2.0, parent=5),   # tip 2
+    ]
+    return RobotTree("three_tip", j, [1, 3, 6])
+
+
+def floating_arm() -> RobotTree:
+    """A floating base (7 variables, src/forward_kinematics.cpp:64-70) carrying a 2-joint arm."""
+    R, F = JOINT_REVOLUTE, JOINT_FIXED
+    j = [
+        Joint("world_joint", JOINT_FLOATING, (0, 0, 0.1), (0, 0, 0), (0, 0, 0), -1.0, 1.0, 0.0, parent=-1),
+        Joint("j1", R, (0, 0, 0.2), (0, 0, 0), (0, 1, 0), -2.0, 2.0, 1.0, parent=0),
+        Joint("j2", R, (0.3, 0, 0), (0, 0, 0), (0, 0, 1), -2.0, 2.0, 1.0, parent=1),
+        Joint("tool", F, (0.2, 0, 0), (0, 0, 0), parent=2),
+    ]
+    return RobotTree("floating_arm", j, [3])
+
+
+def planar_arm() -> RobotTree:
+    """A planar base (x, y, theta; src/forward_kinematics.cpp:71-79) with unbounded translation (MoveIt's default)
+    carrying a 3-joint arm."""
+    R, F = JOINT_REVOLUTE, JOINT_FIXED
+    j = [
+        Joint("base_joint", JOINT_PLANAR, (0, 0, 0.05), (0, 0, 0), (0, 0, 0), velocity=0.5, continuous=True, parent=-1),
+        Joint("j1", R, (0.1, 0, 0.3), (0, 0, 0), (0, 0, 1), -2.5, 2.5, 1.0, parent=0),
+        Joint("j2", R, (0.3, 0, 0), (0, 0, 0), (0, 1, 0), -2.0, 2.0, 1.0, parent=1),
+        Joint("j3", R, (0.25, 0, 0), (0, 0, 0), (0, 1, 0), -2.0, 2.0, 1.0, parent=2),
+        Joint("tool", F, (0.1, 0, 0), (0, 0, 0), parent=3),
+    ]
+    return RobotTree("planar_arm", j, [4])
+
+
+def mimic_arm() -> RobotTree:
+    """A serial arm whose third joint mimics the second (multiplier -0.5, offset 0.1): 3 variables for 4 moving
+    joints (/root/reference/src/robot.cpp:145-147 skips mimic joints; MoveIt's FK drives them from their master)."""
+    R, F = JOINT_REVOLUTE, JOINT_FIXED
+    j = [
+        Joint("j0", R, (0, 0, 0.2), (0, 0, 0), (0, 0, 1), -2.5, 2.5, 1.0, parent=-1),
+        Joint("j1", R, (0.1, 0, 0.1), (0, 0, 0), (0, 1, 0), -1.5, 1.5, 1.0, parent=0),
+        Joint("j1_mimic", R, (0.3, 0, 0), (0, 0, 0), (0, 1, 0), -1.5, 1.5, 1.0, parent=1, mimic_of=1, mimic_factor=-0.5,
+              mimic_offset=0.1),
+        Joint("j2", R, (0.3, 0, 0), (0, 0, 0), (1, 0, 0), -3.0, 3.0, 1.0, parent=2),
+        Joint("tool", F, (0.15, 0, 0), (0, 0, 0), parent=3),
+    ]
+    return RobotTree("mimic_arm", j, [4])
+
+
+TREES = {"two_arm": two_arm, "three_tip": three_tip, "floating_arm": floating_arm, "planar_arm": planar_arm,
+         "mimic_arm": mimic_arm}
 
 ROBOTS = {"single": single, "single_prismatic": single_prismatic, "panda": panda, "ur5": ur5, "fetch": fetch, "rr": rr, "skew6": skew6, "snake16": snake16}

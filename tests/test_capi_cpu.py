@@ -106,7 +106,9 @@ def test_status_strings_and_no_device():
 def test_chain_signatures():
     """select_spec: the most specific compiled chain signature each fixture robot matches (host-side)."""
     expect = {"panda": "all-z 7R, x-rotation origins (static)", "ur5": "y-rotation origins", "fetch": "identity origins",
-              "rr": "identity origins", "skew6": "generic", "snake16": "generic", "single": "x-rotation origins"}  # no origin after the first joint: vacuously any pattern
+              "rr": "identity origins", "skew6": "generic", "snake16": "generic",
+              "single": "generic",  # a general-axis joint: the origin-pattern kernels carry no out-of-line joint path
+              "single_prismatic": "x-rotation origins"}  # no origin after the first joint: vacuously any pattern
     for name, sig in expect.items():
         assert capi.Robot(robots.ROBOTS[name]()).chain_signature() == sig, name
 

@@ -237,3 +237,20 @@ def test_memetic_species_parity(solvers, name, kw, B, mapping, monkeypatch):
     got = solver.solve_batch(gp, goal, seed, first_problem_index=first)
     check_solve(got, ref, f"{name} {kw}")
     assert 0 < (ref["error_code"] == 1).sum()
+
+
+def test_sub_batches_reproduce_the_undivided_solve(solvers, monkeypatch):
+    """PIK_SUB_BATCHES (experiment): the batch cut into sub-batches on streams of their own gives the bits of the
+    undivided batch (RNG keyed by the global problem index), species included."""
+    chain, orobot, solver = solvers("panda")
+    B = 310
+    goal = orc.make_targets(orobot, B)
+    seed = np.array(robots.PANDA_HOME)
+    for kw in (dict(memetic_population_size=16, memetic_max_generations=30),
+               dict(memetic_population_size=16, memetic_max_generations=20, memetic_num_threads=3)):
+        op, gp = both_params(mode="global", **kw)
+        ref = orc.solve_batch(orobot, op, goal, seed, first_problem_index=77)
+        for k in ("3", "8"):
+            monkeypatch.setenv("PIK_SUB_BATCHES", k)
+            check_solve(solver.solve_batch(gp, goal, seed, first_problem_index=77), ref, f"sub-batches {k} {kw}")
+            assert solver.stats().solved == (ref["error_code"] == 1).sum()
