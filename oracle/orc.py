@@ -303,6 +303,24 @@ def solve_batch(robot: Robot, params: Params, goal_pose: np.ndarray, seed: np.nd
     return dict(solution=sol, error_code=err, cost=cst, iterations=its, evals=ev.value)
 
 
+def solve_batch_reference_structure(robot: Robot, params: Params, goal_pose: np.ndarray, seed: np.ndarray,
+                                    first_problem_index: int = 0):
+    """Baseline A (timing only): one solve at a time, E gradient-descent threads per generation behind one FK mutex."""
+    goal_pose = np.ascontiguousarray(goal_pose, dtype=np.float64)
+    B = goal_pose.shape[0]
+    n = robot.n
+    seed = np.ascontiguousarray(seed, dtype=np.float64)
+    stride = 0 if seed.ndim == 1 or seed.shape[0] == 1 else n
+    sol = np.zeros((B, n))
+    err = np.zeros(B, dtype=np.int32)
+    cst = np.zeros(B)
+    its = np.zeros(B, dtype=np.int32)
+    lib().orc_solve_batch_reference_structure(C.byref(robot), C.byref(params), C.c_int64(B), C.c_int64(first_problem_index),
+                                              _dp(goal_pose.reshape(-1)), _dp(seed.reshape(-1)), C.c_int64(stride),
+                                              _dp(sol.reshape(-1)), _ip(err), _dp(cst), _ip(its))
+    return dict(solution=sol, error_code=err, cost=cst, iterations=its)
+
+
 def eval_cost_batch(robot: Robot, params: Params, goal_pose: np.ndarray, seed: np.ndarray, q: np.ndarray):
     goal_pose = np.ascontiguousarray(goal_pose, dtype=np.float64)
     q = np.ascontiguousarray(q, dtype=np.float64)

@@ -722,10 +722,13 @@ static int goal_costs(const orc_problem* pb, const double* q, double out[3]) {
     return n;
 }
 
-/* goal.cpp:188-203 */
-double orc_cost(const orc_problem* pb, const double* q) {
+/* goal.cpp:188-203.  fk_mutex (optional): the lock the reference's FK closure takes around the shared RobotState
+ * (fk_moveit.cpp:21); only the reference-structure baseline passes one. */
+static double cost_locked(const orc_problem* pb, const double* q, pthread_mutex_t* fk_mutex) {
     double R[ORC_MAX_TIPS][9], t[ORC_MAX_TIPS][3];
+    if (fk_mutex) pthread_mutex_lock(fk_mutex);
     orc_fk_tips(pb->robot, q, &R[0][0], &t[0][0]);
+    if (fk_mutex) pthread_mutex_unlock(fk_mutex);
     double pose_cost = 0.0; /* std::accumulate over the tips, goal.cpp:192-196 */
     for (int i = 0; i < pb->robot->n_tips; ++i)
         pose_cost = pose_cost + pose_cost_q(pb->goal_t[i], pb->goal_q[i], t[i], R[i], pb->params->position_scale,
@@ -736,6 +739,8 @@ double orc_cost(const orc_problem* pb, const double* q) {
     for (int i = 0; i < ng; ++i) goal_cost = goal_cost + g[i];
     return pose_cost + goal_cost;
 }
+
+double orc_cost(const orc_problem* pb, const double* q) { return cost_locked(pb, q, NULL); }
 
 /* goal.cpp:163-186 with thresholds enabled as pick_ik_plugin.cpp:97-106 */
 int orc_is_solution(const orc_problem* pb, const double* q) {
@@ -764,11 +769,12 @@ typedef struct {
     const orc_problem* pb;
     uint64_t evals;
     uint32_t gd_steps;
+    pthread_mutex_t* fk_mutex; /* reference-structure baseline only */
 } orc_ctx;
 
 static double cost_counted(orc_ctx* cx, const double* q) {
     cx->evals++;
-    return orc_cost(cx->pb, q);
+    return cost_locked(cx->pb, q, cx->fk_mutex);
 }
 
 /* ik_gradient.cpp:24-94 */
@@ -816,7 +822,7 @@ static int gd_step(orc_ctx* cx, double* gradient, double* working, double* local
 
 int orc_gd_step(const orc_problem* pb, double* gradient, double* working, double* local,
                 double* best, double* local_cost, double* best_cost) {
-    orc_ctx cx = {pb, 0, 0};
+    orc_ctx cx = {pb, 0, 0, NULL};
     return gd_step(&cx, gradient, working, local, best, local_cost, best_cost);
 }
 
@@ -825,7 +831,7 @@ void orc_ik_gradient(const orc_problem* pb, const double* initial_guess, orc_res
     const orc_params* p = pb->params;
     const int n = pb->robot->n;
     memset(out, 0, sizeof(*out));
-    orc_ctx cx = {pb, 0, 0};
+    orc_ctx cx = {pb, 0, 0, NULL};
     if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, initial_guess)) {
         out->found = 1;
         memcpy(out->solution, initial_guess, n * sizeof(double));
@@ -923,23 +929,26 @@ static void init_population(orc_memetic* m, const double* initial_guess) {
 }
 
 /* ik_memetic.cpp:66-91 */
-static void gradient_descent(orc_memetic* m, int i) {
-    const orc_params* p = m->cx.pb->params;
+static void gradient_descent_ctx(orc_memetic* m, int i, orc_ctx* cx);
+static void gradient_descent(orc_memetic* m, int i) { gradient_descent_ctx(m, i, &m->cx); }
+
+static void gradient_descent_ctx(orc_memetic* m, int i, orc_ctx* cx) {
+    const orc_params* p = cx->pb->params;
     orc_individual* ind = &m->pop[i];
     const int n = m->n;
     double gradient[ORC_MAX_VARS] = {0}, working[ORC_MAX_VARS], local[ORC_MAX_VARS], best[ORC_MAX_VARS];
-    double local_cost = cost_counted(&m->cx, ind->genes), best_cost = local_cost;
+    double local_cost = cost_counted(cx, ind->genes), best_cost = local_cost;
     for (int k = 0; k < n; ++k) working[k] = local[k] = best[k] = ind->genes[k];
     int num_iterations = 0;
     double previous_cost = 0.0;
     while (num_iterations < p->memetic_gd_max_iters) {
-        gd_step(&m->cx, gradient, working, local, best, &local_cost, &best_cost);
+        gd_step(cx, gradient, working, local, best, &local_cost, &best_cost);
         if (fabs(local_cost - previous_cost) <= p->gd_min_cost_delta) break;
         previous_cost = local_cost;
         num_iterations++;
     }
     for (int k = 0; k < n; ++k) ind->genes[k] = best[k];
-    ind->fitness = cost_counted(&m->cx, ind->genes);
+    ind->fitness = cost_counted(cx, ind->genes);
     for (int k = 0; k < n; ++k) ind->gradient[k] = gradient[k];
 }
 
@@ -1245,6 +1254,100 @@ void orc_ik_memetic_species(const orc_problem* pb, const double* initial_guess, 
     }
     for (int s = 0; s < S; ++s) memetic_end(&ms[s]);
     free(ms); free(done); free(found); free(iters); free(phase);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Baseline A: the reference's own execution structure, for timing only.  One solve at a time; in
+ * every generation the elites' gradient descents run in E freshly created threads (ik_memetic.cpp:230-239) that
+ * share one FK mutex (fk_moveit.cpp:21, pick_ik_plugin.hpp:21); reproduce, sort and the tests run on the calling
+ * thread, whose cost evaluations take the same lock.  The results are those of orc_ik_memetic (the elites are
+ * independent of one another).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    orc_memetic* m;
+    int elite;
+    orc_ctx cx;
+} elite_job;
+
+static void* elite_thread(void* arg) {
+    elite_job* job = (elite_job*)arg;
+    gradient_descent_ctx(job->m, job->elite, &job->cx);
+    return NULL;
+}
+
+static void ik_memetic_reference_structure(const orc_problem* pb, const double* initial_guess,
+                                           uint32_t problem_index, orc_result* out) {
+    const orc_params* p = pb->params;
+    const int n = pb->robot->n;
+    memset(out, 0, sizeof(*out));
+    if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, initial_guess)) {
+        out->found = 1;
+        memcpy(out->solution, initial_guess, n * sizeof(double));
+        out->cost = orc_cost(pb, initial_guess);
+        return;
+    }
+    pthread_mutex_t fk_mutex;
+    pthread_mutex_init(&fk_mutex, NULL);
+    orc_memetic m;
+    memetic_begin(&m, pb, initial_guess, problem_index, 0);
+    m.cx.fk_mutex = &fk_mutex;
+    elite_job jobs[32];
+    pthread_t threads[32];
+    int iter = 0, found = 0;
+    while (iter < p->memetic_max_generations) {
+        for (int i = 0; i < m.E; ++i) {
+            jobs[i].m = &m;
+            jobs[i].elite = i;
+            memset(&jobs[i].cx, 0, sizeof(orc_ctx));
+            jobs[i].cx.pb = pb;
+            jobs[i].cx.fk_mutex = &fk_mutex;
+            pthread_create(&threads[i], NULL, elite_thread, &jobs[i]);
+        }
+        for (int i = 0; i < m.E; ++i) {
+            pthread_join(threads[i], NULL);
+            m.cx.evals += jobs[i].cx.evals;
+            m.cx.gd_steps += jobs[i].cx.gd_steps;
+        }
+        reproduce(&m, (uint32_t)iter);
+        sort_population(&m);
+        if (p->stop_optimization_on_valid_solution && orc_is_solution(pb, m.best.genes)) {
+            found = 1;
+            break;
+        }
+        if (check_wipeout(&m)) {
+            m.wipeouts++;
+            init_population(&m, m.best.genes);
+        }
+        iter++;
+    }
+    if (!found) found = memetic_tail_found(&m);
+    out->found = found;
+    out->iterations = iter;
+    out->cost = m.best.fitness;
+    out->evals = m.cx.evals;
+    out->wipeouts = m.wipeouts;
+    out->gd_steps = m.cx.gd_steps;
+    memcpy(out->solution, m.best.genes, n * sizeof(double));
+    memetic_end(&m);
+    pthread_mutex_destroy(&fk_mutex);
+}
+
+void orc_solve_batch_reference_structure(const orc_robot* robot, const orc_params* params, int64_t B,
+                                         int64_t first_problem_index, const double* goal_pose, const double* seed,
+                                         int64_t seed_stride, double* solution, int32_t* error_code, double* cost,
+                                         int32_t* iterations) {
+    const int n = robot->n;
+    for (int64_t b = 0; b < B; ++b) {
+        const double* sd = seed + b * seed_stride;
+        orc_problem pb;
+        orc_problem_init(&pb, robot, params, goal_pose + 7 * robot->n_tips * b, sd);
+        orc_result res;
+        ik_memetic_reference_structure(&pb, sd, (uint32_t)(first_problem_index + b), &res);
+        error_code[b] = res.found ? 1 : -31;
+        memcpy(solution + b * n, res.found ? res.solution : sd, n * sizeof(double));
+        if (cost) cost[b] = res.cost;
+        if (iterations) iterations[b] = res.iterations;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------

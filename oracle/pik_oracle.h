@@ -214,6 +214,14 @@ void orc_solve_batch(const orc_robot* robot, const orc_params* params, int64_t B
                      int64_t seed_stride, double* solution, int32_t* error_code, double* cost,
                      int32_t* iterations, uint64_t* evals_total, int n_threads);
 
+/* Baseline A (timing only): the reference's execution structure -- one solve at a time, the elites' gradient descents
+ * of every generation in E new threads behind one FK mutex (ik_memetic.cpp:230-239, fk_moveit.cpp:21).  Global mode,
+ * one species.  Same results as orc_solve_batch. */
+void orc_solve_batch_reference_structure(const orc_robot* robot, const orc_params* params, int64_t B,
+                                         int64_t first_problem_index, const double* goal_pose, const double* seed,
+                                         int64_t seed_stride, double* solution, int32_t* error_code, double* cost,
+                                         int32_t* iterations);
+
 /* Batched FK + cost (checker for pik_eval_cost): q [B][n], goal_pose [B][n_tips][7], tip_pose [B][n_tips][7] */
 void orc_eval_cost_batch(const orc_robot* robot, const orc_params* params, int64_t B,
                          const double* goal_pose, const double* seed, int64_t seed_stride,

@@ -143,18 +143,52 @@ struct PickIKPlugin::Impl {
     std::vector<std::string> tip_frames;
     std::vector<std::string> joint_names, link_names;
     pik_robot* robot = nullptr;
-    pik_solver* solver = nullptr;
+    int device = 0;
     int n = 0;
+    int n_tips = 1;
+    // searchPositionIK is const and re-entrant in the reference (it serialises on the FK mutex only): every call in
+    // flight takes a solver (own stream, own device buffers) from this pool and puts it back
+    mutable std::vector<pik_solver*> idle_solvers;
     // constant transform model frame <- base frame (identity unless base_frame is a link behind fixed joints)
     double base_R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     double base_t[3] = {0, 0, 0};
     bool base_identity = true;
     Params params;
-    mutable std::mutex mutex;  // one in-flight call per solver handle (the reference serialises FK on fk_mutex_)
+    mutable std::mutex mutex;  // guards params, the pool and last_error
     mutable std::string last_error;
 
+    pik_solver* take_solver() const {
+        {
+            std::lock_guard<std::mutex> lock(mutex);
+            if (!idle_solvers.empty()) {
+                pik_solver* s = idle_solvers.back();
+                idle_solvers.pop_back();
+                return s;
+            }
+        }
+        pik_solver* s = nullptr;
+        int const rc = pik_solver_create(robot, device, nullptr, &s);
+        if (rc != PIK_OK) {
+            set_error(std::string("pik_solver_create: ") + pik_status_string(rc));
+            return nullptr;
+        }
+        return s;
+    }
+    void give_solver(pik_solver* s) const {
+        std::lock_guard<std::mutex> lock(mutex);
+        idle_solvers.push_back(s);
+    }
+    void set_error(std::string const& e) const {
+        std::lock_guard<std::mutex> lock(mutex);
+        last_error = e;
+    }
+    void drop_solvers() {
+        for (pik_solver* s : idle_solvers) pik_solver_destroy(s);
+        idle_solvers.clear();
+    }
+
     ~Impl() {
-        if (solver) pik_solver_destroy(solver);
+        drop_solvers();
         if (robot) pik_robot_destroy(robot);
     }
 };
@@ -227,41 +261,70 @@ bool PickIKPlugin::initialize(compat::ChainModel const& model, std::string const
         d.last_error = "failed to get joint model group " + group_name;
         return false;
     }
-    if (model.joints.empty() || model.joints.size() != model.joint_names.size() ||
-        model.joints.size() != model.link_names.size()) {
+    size_t const nj = model.joints.size();
+    if (nj == 0 || nj != model.joint_names.size() || nj != model.link_names.size() ||
+        (!model.parent.empty() && model.parent.size() != nj) ||
+        (!model.mimic_of.empty() && (model.mimic_of.size() != nj || model.mimic_factor.size() != nj || model.mimic_offset.size() != nj))) {
         d.last_error = "malformed chain model";
+        return false;
+    }
+    if (tip_frames.empty() || tip_frames.size() > PIK_MAX_TIPS) {
+        d.last_error = "between 1 and " + std::to_string(PIK_MAX_TIPS) + " tip frames are supported";
         return false;
     }
     // link_names_ = tip_frames_ (src/pick_ik_plugin.cpp:62); every tip must be a link of the model, else
     // std::invalid_argument (src/pick_ik_plugin.cpp:65-67 via get_link_indices, src/robot.cpp:107-120)
     d.link_names = tip_frames;
-    std::vector<size_t> tip_idx;
+    std::vector<int32_t> tip_joint;
     for (auto const& tip : tip_frames) {
         auto it = std::find(model.link_names.begin(), model.link_names.end(), tip);
         if (it == model.link_names.end()) throw std::invalid_argument("link not found: " + tip);
-        tip_idx.push_back(static_cast<size_t>(it - model.link_names.begin()));
+        tip_joint.push_back(static_cast<int32_t>(it - model.link_names.begin()));
     }
-    if (tip_idx.size() != 1) {
-        d.last_error = "exactly one tip frame is supported by the batched engine";
-        return false;
-    }
-    size_t const n_joints = tip_idx[0] + 1;  // the chain up to and including the tip link's parent joint
-    // joint names of the group's active joints (src/pick_ik_plugin.cpp:52-58)
+    auto parent_of = [&](size_t j) { return model.parent.empty() ? static_cast<int32_t>(j) - 1 : model.parent[j]; };
+    // the joints between the tips and the root are the ones in use (get_active_variable_indices, src/robot.cpp:122-160)
+    std::vector<char> used(nj, 0);
+    for (int32_t t : tip_joint)
+        for (int32_t j = t; j >= 0; j = parent_of(static_cast<size_t>(j))) used[static_cast<size_t>(j)] = 1;
+    // compact to the used joints (order kept: parents stay in front of their children)
+    std::vector<pik_joint_desc> joints;
+    std::vector<int32_t> parent, mimic_of, new_index(nj, -1);
+    std::vector<double> mimic_factor, mimic_offset;
+    bool any_mimic = false;
     d.joint_names.clear();
-    for (size_t j = 0; j < n_joints; ++j)
-        if (model.joints[j].type != PIK_JOINT_FIXED) d.joint_names.push_back(model.joint_names[j]);
-    // base frame: the model frame itself, or a chain link that only fixed joints separate from it
+    for (size_t j = 0; j < nj; ++j) {
+        if (!used[j]) continue;
+        new_index[j] = static_cast<int32_t>(joints.size());
+        joints.push_back(model.joints[j]);
+        int32_t const p = parent_of(j);
+        parent.push_back(p >= 0 ? new_index[static_cast<size_t>(p)] : -1);
+        int32_t const m = model.mimic_of.empty() ? -1 : model.mimic_of[j];
+        if (m >= 0 && (static_cast<size_t>(m) >= nj || !used[static_cast<size_t>(m)] || new_index[static_cast<size_t>(m)] < 0)) {
+            d.last_error = "joint " + model.joint_names[j] + " mimics a joint outside the chains of the tip frames";
+            return false;
+        }
+        mimic_of.push_back(m >= 0 ? new_index[static_cast<size_t>(m)] : -1);
+        mimic_factor.push_back(m >= 0 ? model.mimic_factor[j] : 1.0);
+        mimic_offset.push_back(m >= 0 ? model.mimic_offset[j] : 0.0);
+        any_mimic = any_mimic || m >= 0;
+        // joint names of the group's active joints (src/pick_ik_plugin.cpp:52-58)
+        if (model.joints[j].type != PIK_JOINT_FIXED && m < 0) d.joint_names.push_back(model.joint_names[j]);
+    }
+    for (int32_t& t : tip_joint) t = new_index[static_cast<size_t>(t)];
+    // base frame: the model frame itself, or a link that only fixed joints separate from it
     d.base_identity = true;
     if (!base_frame.empty() && base_frame != model.model_frame) {
         auto it = std::find(model.link_names.begin(), model.link_names.end(), base_frame);
         if (it == model.link_names.end()) {
-            d.last_error = "base frame " + base_frame + " is not a link of the chain";
+            d.last_error = "base frame " + base_frame + " is not a link of the model";
             return false;
         }
-        size_t const upto = static_cast<size_t>(it - model.link_names.begin());
+        std::vector<size_t> path;
+        for (int32_t j = static_cast<int32_t>(it - model.link_names.begin()); j >= 0; j = parent_of(static_cast<size_t>(j)))
+            path.push_back(static_cast<size_t>(j));
         double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
-        for (size_t j = 0; j <= upto; ++j) {
-            auto const& jd = model.joints[j];
+        for (size_t a = path.size(); a-- > 0;) {
+            auto const& jd = model.joints[path[a]];
             if (jd.type != PIK_JOINT_FIXED) {
                 d.last_error = "base frame " + base_frame + " moves with the group: unsupported";
                 return false;
@@ -279,19 +342,23 @@ bool PickIKPlugin::initialize(compat::ChainModel const& model, std::string const
         std::memcpy(d.base_t, t, sizeof(t));
         d.base_identity = false;
     }
-    if (d.solver) { pik_solver_destroy(d.solver); d.solver = nullptr; }
+    d.drop_solvers();
     if (d.robot) { pik_robot_destroy(d.robot); d.robot = nullptr; }
-    int rc = pik_robot_create(model.joints.data(), static_cast<int32_t>(n_joints), &d.robot);  // Robot::from, :68
+    // Robot::from, src/pick_ik_plugin.cpp:68
+    int rc = pik_robot_create_tree(joints.data(), static_cast<int32_t>(joints.size()), parent.data(), tip_joint.data(),
+                                   static_cast<int32_t>(tip_joint.size()), any_mimic ? mimic_of.data() : nullptr,
+                                   any_mimic ? mimic_factor.data() : nullptr, any_mimic ? mimic_offset.data() : nullptr,
+                                   &d.robot);
     if (rc != PIK_OK) {
-        d.last_error = std::string("pik_robot_create: ") + pik_status_string(rc);
+        d.last_error = std::string("pik_robot_create_tree: ") + pik_status_string(rc);
         return false;
     }
     d.n = pik_robot_num_variables(d.robot);
-    rc = pik_solver_create(d.robot, device, nullptr, &d.solver);
-    if (rc != PIK_OK) {
-        d.last_error = std::string("pik_solver_create: ") + pik_status_string(rc);
-        return false;
-    }
+    d.n_tips = pik_robot_num_tips(d.robot);
+    d.device = device;
+    pik_solver* first = d.take_solver();  // fails here, not in the first solve, when there is no device
+    if (!first) return false;
+    d.give_solver(first);
     return true;
 }
 
@@ -321,49 +388,64 @@ long PickIKPlugin::searchPositionIKBatch(std::vector<Pose> const& ik_poses,
                                          std::vector<std::vector<double>> const& seeds,
                                          std::vector<std::vector<double>>& solutions,
                                          std::vector<MoveItErrorCodes>& error_codes,
-                                         KinematicsQueryOptions const& options) const {
+                                         KinematicsQueryOptions const& options, std::vector<double>* costs,
+                                         unsigned long long rng_seed) const {
     Impl const& d = *impl_;
-    std::lock_guard<std::mutex> lock(d.mutex);
-    d.last_error.clear();
-    if (!d.solver) { d.last_error = "not initialized"; return -1; }
-    int64_t const B = static_cast<int64_t>(ik_poses.size());
-    if (static_cast<int64_t>(seeds.size()) != B && seeds.size() != 1) { d.last_error = "one seed per pose (or one for all)"; return -1; }
+    if (!d.robot) { d.set_error("not initialized"); return -1; }
+    int const n = d.n, T = d.n_tips;
+    if (ik_poses.size() % static_cast<size_t>(T) != 0) { d.set_error("one pose per tip frame and problem expected"); return -1; }
+    int64_t const B = static_cast<int64_t>(ik_poses.size()) / T;
+    if (static_cast<int64_t>(seeds.size()) != B && seeds.size() != 1) { d.set_error("one seed per problem (or one for all)"); return -1; }
+    Params params;
+    {
+        std::lock_guard<std::mutex> lock(d.mutex);  // the reference re-reads its parameters on every solve (:86)
+        params = d.params;
+    }
     pik_params pp;
-    if (!to_pik_params(d.params, options.return_approximate_solution, pp)) {
-        d.last_error = "Invalid solver mode: " + d.params.mode;
-        std::fprintf(stderr, "[pick_ik] %s\n", d.last_error.c_str());
+    if (!to_pik_params(params, options.return_approximate_solution, pp)) {
+        d.set_error("Invalid solver mode: " + params.mode);
+        std::fprintf(stderr, "[pick_ik] Invalid solver mode: %s\n", params.mode.c_str());
         return -1;
     }
-    int const n = d.n;
-    std::vector<double> goal(static_cast<size_t>(B) * 7), seed(seeds.size() * n), sol(static_cast<size_t>(B) * n), cost(B);
+    if (rng_seed != 0) pp.rng_seed = rng_seed;
+    std::vector<double> goal(static_cast<size_t>(B) * 7 * T), seed(seeds.size() * n), sol(static_cast<size_t>(B) * n), cost(B);
     std::vector<int32_t> err(B), its(B);
-    for (int64_t b = 0; b < B; ++b) pose_to_goal(d.base_identity, d.base_R, d.base_t, ik_poses[b], &goal[7 * b]);
+    for (size_t k = 0; k < ik_poses.size(); ++k) pose_to_goal(d.base_identity, d.base_R, d.base_t, ik_poses[k], &goal[7 * k]);
     for (size_t b = 0; b < seeds.size(); ++b) {
-        if (static_cast<int>(seeds[b].size()) != n) { d.last_error = "seed size != number of variables"; return -1; }
+        if (static_cast<int>(seeds[b].size()) != n) { d.set_error("seed size != number of variables"); return -1; }
         std::copy(seeds[b].begin(), seeds[b].end(), seed.begin() + b * n);
     }
     int64_t const stride = seeds.size() == 1 ? 0 : n;
-    int rc = pik_solve_batch(d.solver, &pp, B, 0, goal.data(), seed.data(), stride, sol.data(), err.data(), cost.data(),
+    pik_solver* solver = d.take_solver();
+    if (!solver) return -1;
+    int rc = pik_solve_batch(solver, &pp, B, 0, goal.data(), seed.data(), stride, sol.data(), err.data(), cost.data(),
                              its.data(), PIK_MEM_HOST);
     if (rc != PIK_OK) {
-        d.last_error = std::string("pik_solve_batch: ") + pik_status_string(rc) + " " + pik_solver_last_error(d.solver);
+        d.set_error(std::string("pik_solve_batch: ") + pik_status_string(rc) + " " + pik_solver_last_error(solver));
+        d.give_solver(solver);
         return -1;
     }
     // approximate-solution gating (src/pick_ik_plugin.cpp:222-267), per problem
     std::vector<int32_t> approx_ok;
     if (options.return_approximate_solution && B > 0) {
         pik_params ap = pp;
-        ap.cost_threshold = d.params.approximate_solution_cost_threshold;
-        if (d.params.approximate_solution_cost_threshold <= 0.0)  // goals.clear(), :240-242
+        ap.cost_threshold = params.approximate_solution_cost_threshold;
+        if (params.approximate_solution_cost_threshold <= 0.0)  // goals.clear(), :240-242
             ap.center_joints_weight = ap.avoid_joint_limits_weight = ap.minimal_displacement_weight = 0.0;
         // the reference tests `frame_tests` (the strict thresholds), not approx_frame_tests (:244-248): replicated
         approx_ok.resize(B);
-        rc = pik_eval_cost(d.solver, &ap, B, goal.data(), seed.data(), stride, sol.data(), nullptr, approx_ok.data(),
+        rc = pik_eval_cost(solver, &ap, B, goal.data(), seed.data(), stride, sol.data(), nullptr, approx_ok.data(),
                            nullptr, PIK_MEM_HOST);
-        if (rc != PIK_OK) { d.last_error = std::string("pik_eval_cost: ") + pik_status_string(rc); return -1; }
+        if (rc != PIK_OK) {
+            d.set_error(std::string("pik_eval_cost: ") + pik_status_string(rc));
+            d.give_solver(solver);
+            return -1;
+        }
     }
+    d.give_solver(solver);
     solutions.assign(B, std::vector<double>());
     error_codes.assign(B, MoveItErrorCodes());
+    if (costs) costs->assign(cost.begin(), cost.end());
     long solved = 0;
     for (int64_t b = 0; b < B; ++b) {
         double const* sd = &seed[stride ? b * n : 0];
@@ -371,9 +453,9 @@ long PickIKPlugin::searchPositionIKBatch(std::vector<Pose> const& ik_poses,
         error_codes[b].val = err[b] == PIK_SUCCESS ? MoveItErrorCodes::SUCCESS : MoveItErrorCodes::NO_IK_SOLUTION;
         if (options.return_approximate_solution) {
             bool valid = approx_ok[b] != 0;
-            if (valid && d.params.approximate_solution_joint_threshold > 0.0)
+            if (valid && params.approximate_solution_joint_threshold > 0.0)
                 for (int i = 0; i < n; ++i)
-                    if (std::fabs(solutions[b][i] - sd[i]) > d.params.approximate_solution_joint_threshold) { valid = false; break; }
+                    if (std::fabs(solutions[b][i] - sd[i]) > params.approximate_solution_joint_threshold) { valid = false; break; }
             if (!valid) {
                 error_codes[b].val = MoveItErrorCodes::NO_IK_SOLUTION;
                 solutions[b].assign(sd, sd + n);
@@ -387,39 +469,48 @@ long PickIKPlugin::searchPositionIKBatch(std::vector<Pose> const& ik_poses,
 bool PickIKPlugin::searchPositionIK(std::vector<Pose> const& ik_poses, std::vector<double> const& ik_seed_state,
                                     double timeout, std::vector<double> const& /*consistency_limits*/,
                                     std::vector<double>& solution, compat::IKCallbackFn const& solution_callback,
-                                    MoveItErrorCodes& error_code, KinematicsQueryOptions const& options) const {
-    Impl& d = *impl_;
+                                    compat::IKCostFn const& cost_function, MoveItErrorCodes& error_code,
+                                    KinematicsQueryOptions const& options, compat::RobotState const* /*context_state*/) const {
+    Impl const& d = *impl_;
     if (ik_poses.size() != d.tip_frames.size()) {  // one pose per tip frame (assert in src/goal.cpp:169)
-        d.last_error = "one pose per tip frame expected";
+        d.set_error("one pose per tip frame expected");
+        error_code.val = MoveItErrorCodes::NO_IK_SOLUTION;
+        solution = ik_seed_state;
         return false;
     }
-    Params const base = d.params;
+    if (cost_function) {
+        // src/pick_ik_plugin.cpp:130-135 adds one goal per pose that calls back into host code with a RobotState
+        // (src/goal.cpp:146-161); the device kernels cannot evaluate it and silently ignoring it would change what is
+        // optimised, so the call is refused with a defined status
+        d.set_error("a custom IKCostFn is a host callback and is not supported by the GPU solver");
+        std::fprintf(stderr, "[pick_ik] %s\n", "a custom IKCostFn is a host callback and is not supported by the GPU solver");
+        error_code.val = MoveItErrorCodes::NO_IK_SOLUTION;
+        solution = ik_seed_state;
+        return false;
+    }
+    Params base;
+    {
+        std::lock_guard<std::mutex> lock(d.mutex);
+        base = d.params;
+    }
     bool found_valid_solution = false;
     auto const t0 = std::chrono::steady_clock::now();
-    // Optimize until a valid solution or the timeout (src/pick_ik_plugin.cpp:147-150,162-291).  The
-    // reference retries from the same seed; only its unseeded RNG differs between attempts, which the
-    // attempt number stands in for here.  Local mode is deterministic: one attempt.
+    // Optimize until a valid solution or the timeout (src/pick_ik_plugin.cpp:147-150,162-291).  The reference retries
+    // from the same seed; only its unseeded RNG differs between attempts, which the attempt number stands in for here
+    // (passed down as the random stream of the call: nothing shared is modified).  Local mode is deterministic: one
+    // attempt.
     for (unsigned attempt = 0;; ++attempt) {
-        // memetic_num_threads species (src/ik_memetic.cpp:312-371) = replicas with distinct random streams
-        int const species = (base.mode == "global" && base.memetic_num_threads > 1) ? base.memetic_num_threads : 1;
-        std::vector<Pose> poses(species, ik_poses.front());
         std::vector<std::vector<double>> seeds(1, ik_seed_state), sols;
         std::vector<MoveItErrorCodes> codes;
-        {
-            std::lock_guard<std::mutex> lock(d.mutex);
-            d.params.rng_seed = base.rng_seed + 0x9E3779B97F4A7C15ull * attempt;
+        unsigned long long const stream = base.rng_seed + 0x9E3779B97F4A7C15ull * attempt;
+        long const solved = searchPositionIKBatch(ik_poses, seeds, sols, codes, options, nullptr, stream ? stream : 1);
+        if (solved < 0) {  // invalid mode / engine error (src/pick_ik_plugin.cpp:204-207)
+            error_code.val = MoveItErrorCodes::NO_IK_SOLUTION;
+            solution = ik_seed_state;
+            return false;
         }
-        long const solved = searchPositionIKBatch(poses, seeds, sols, codes, options);
-        {
-            std::lock_guard<std::mutex> lock(d.mutex);
-            d.params.rng_seed = base.rng_seed;
-        }
-        if (solved < 0) return false;  // invalid mode / engine error (src/pick_ik_plugin.cpp:204-207)
-        int pick = 0;
-        for (int s = 0; s < species; ++s)
-            if (codes[s].val == MoveItErrorCodes::SUCCESS) { pick = s; break; }
-        error_code.val = codes[pick].val;
-        solution = codes[pick].val == MoveItErrorCodes::SUCCESS ? sols[pick] : ik_seed_state;  // :209-217
+        error_code.val = codes[0].val;
+        solution = codes[0].val == MoveItErrorCodes::SUCCESS ? sols[0] : ik_seed_state;  // :209-217
         if (solution_callback && error_code.val == MoveItErrorCodes::SUCCESS)  // :270-274; the callback may veto
             solution_callback(ik_poses.front(), solution, error_code);
         found_valid_solution = error_code.val == MoveItErrorCodes::SUCCESS;
@@ -427,6 +518,15 @@ bool PickIKPlugin::searchPositionIK(std::vector<Pose> const& ik_poses, std::vect
         if (found_valid_solution || elapsed >= timeout || base.mode != "global") break;
     }
     return found_valid_solution;
+}
+
+bool PickIKPlugin::searchPositionIK(std::vector<Pose> const& ik_poses, std::vector<double> const& ik_seed_state,
+                                    double timeout, std::vector<double> const& consistency_limits,
+                                    std::vector<double>& solution, compat::IKCallbackFn const& solution_callback,
+                                    MoveItErrorCodes& error_code, KinematicsQueryOptions const& options,
+                                    compat::RobotState const* context_state) const {
+    return searchPositionIK(ik_poses, ik_seed_state, timeout, consistency_limits, solution, solution_callback,
+                            compat::IKCostFn(), error_code, options, context_state);
 }
 
 bool PickIKPlugin::searchPositionIK(Pose const& ik_pose, std::vector<double> const& ik_seed_state, double timeout,
@@ -467,7 +567,7 @@ bool PickIKPlugin::getPositionIK(Pose const&, std::vector<double> const&, std::v
     return false;
 }
 
-void PickIKPlugin::setParams(Params const& p) {
+void PickIKPlugin::setParams(Params const& p) const {
     std::lock_guard<std::mutex> lock(impl_->mutex);
     impl_->params = p;
 }

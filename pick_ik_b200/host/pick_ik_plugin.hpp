@@ -51,14 +51,25 @@ struct KinematicsQueryOptions {
 // kinematics::KinematicsBase::IKCallbackFn
 using IKCallbackFn = std::function<void(Pose const&, std::vector<double> const&, MoveItErrorCodes&)>;
 
+// moveit::core::RobotState / JointModelGroup: only named by the interface (context_state is ignored by the reference,
+// src/pick_ik_plugin.cpp:83; an IKCostFn receives them)
+struct RobotState {};
+struct JointModelGroup {};
+// kinematics::KinematicsBase::IKCostFn
+using IKCostFn = std::function<double(Pose const&, RobotState const&, JointModelGroup const*, std::vector<double> const&)>;
+
 // What the plugin reads from moveit::core::RobotModel + JointModelGroup (src/pick_ik_plugin.cpp:42-68,
-// src/robot.cpp:44-85,107-160): the serial chain of the group from the model root to its tip link.
+// src/robot.cpp:44-85,107-160): the joints of the model from the root down to the tip links of the group -- a serial
+// chain (parent empty) or a tree (parent[j] = index of the joint above joint j, -1 = the model root, parents first).
 struct ChainModel {
     std::string group_name;
     std::string model_frame;               // RobotModel::getModelFrame()
-    std::vector<pik_joint_desc> joints;    // chain order, fixed joints included
+    std::vector<pik_joint_desc> joints;    // parents before children (a chain: chain order), fixed joints included
     std::vector<std::string> joint_names;  // one per entry of `joints`
-    std::vector<std::string> link_names;   // child link of each joint; the last one is the tip link
+    std::vector<std::string> link_names;   // child link of each joint (a chain: the last one is the tip link)
+    std::vector<int32_t> parent;           // empty: a serial chain in joint order
+    std::vector<int32_t> mimic_of;         // empty: no mimic joints; else per joint the joint it follows or -1
+    std::vector<double> mimic_factor, mimic_offset;
 };
 
 // Stand-alone replacement for the RobotModel: the chain base_link -> tip_link of a URDF document
@@ -124,14 +135,24 @@ class PickIKPlugin {
                     std::string const& base_frame, std::vector<std::string> const& tip_frames,
                     double search_discretization, int device = 0);
 
-    // The main overload (include/pick_ik/pick_ik_plugin.hpp:31-41, src/pick_ik_plugin.cpp:73-294).  The
-    // custom IKCostFn of the reference is a host callback over a RobotState and cannot run on the device: not
-    // offered.  consistency_limits and context_state are ignored, as in the reference.
+    // The main overload, signature as include/pick_ik/pick_ik_plugin.hpp:31-41 (src/pick_ik_plugin.cpp:73-294): one
+    // pose per tip frame.  consistency_limits and context_state are ignored, as in the reference.  A non-empty
+    // cost_function is a host callback over a RobotState (src/goal.cpp:146-161) and cannot be evaluated by the device
+    // kernels: the call logs the reason, sets NO_IK_SOLUTION, hands the seed back and returns false.  The method is
+    // const and re-entrant: concurrent callers get solvers of their own from a pool.
+    bool searchPositionIK(std::vector<compat::Pose> const& ik_poses, std::vector<double> const& ik_seed_state,
+                          double timeout, std::vector<double> const& consistency_limits,
+                          std::vector<double>& solution, compat::IKCallbackFn const& solution_callback,
+                          compat::IKCostFn const& cost_function, compat::MoveItErrorCodes& error_code,
+                          compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions(),
+                          compat::RobotState const* context_state = nullptr) const;
+    // include/pick_ik/pick_ik_plugin.hpp:92-102: the same without a cost function
     bool searchPositionIK(std::vector<compat::Pose> const& ik_poses, std::vector<double> const& ik_seed_state,
                           double timeout, std::vector<double> const& consistency_limits,
                           std::vector<double>& solution, compat::IKCallbackFn const& solution_callback,
                           compat::MoveItErrorCodes& error_code,
-                          compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
+                          compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions(),
+                          compat::RobotState const* context_state = nullptr) const;
 
     // Forwarding overloads (include/pick_ik/pick_ik_plugin.hpp:57-102, src/pick_ik_plugin.cpp:314-401)
     bool searchPositionIK(compat::Pose const& ik_pose, std::vector<double> const& ik_seed_state, double timeout,
@@ -150,14 +171,18 @@ class PickIKPlugin {
                           compat::IKCallbackFn const& solution_callback, compat::MoveItErrorCodes& error_code,
                           compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
 
-    // Batched form of the main overload (new): B independent problems, one pose and one seed each, solved in
-    // one pik_solve_batch call.  solutions [B][n]; error_codes [B].  Returns the number of problems solved, or
-    // -1 on an invalid mode / engine error.  Applies the same approximate-solution gating per problem.
+    // Batched form of the main overload (new): B independent problems solved in one pik_solve_batch call.  ik_poses
+    // holds the poses of problem b at [b * n_tips, (b + 1) * n_tips), one per tip frame; one seed per problem or one for
+    // all.  solutions [B][n]; error_codes [B]; costs (optional) [B] the cost of the best individual found.  rng_seed:
+    // the random stream of this call (the reference's RNG is unseeded; Params::rng_seed when 0).  Returns the number
+    // of problems solved, or -1 on an invalid mode / engine error.  Applies the same approximate-solution gating per
+    // problem.  memetic_num_threads species per problem run inside the engine (src/ik_memetic.cpp:315-370).
     long searchPositionIKBatch(std::vector<compat::Pose> const& ik_poses,
                                std::vector<std::vector<double>> const& ik_seed_states,
                                std::vector<std::vector<double>>& solutions,
                                std::vector<compat::MoveItErrorCodes>& error_codes,
-                               compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions()) const;
+                               compat::KinematicsQueryOptions const& options = compat::KinematicsQueryOptions(),
+                               std::vector<double>* costs = nullptr, unsigned long long rng_seed = 0) const;
 
     std::vector<std::string> const& getJointNames() const;  // src/pick_ik_plugin.cpp:296
     std::vector<std::string> const& getLinkNames() const;   // src/pick_ik_plugin.cpp:298
@@ -166,7 +191,7 @@ class PickIKPlugin {
     bool getPositionIK(compat::Pose const&, std::vector<double> const&, std::vector<double>&,
                        compat::MoveItErrorCodes&, compat::KinematicsQueryOptions const&) const;
 
-    void setParams(Params const& p);
+    void setParams(Params const& p) const;  // (const: the parameters are re-read before every solve, src/pick_ik_plugin.cpp:86)
     Params const& getParams() const;
     std::string const& lastError() const;
 

@@ -8,6 +8,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../pick_ik_b200/host/pick_ik_plugin.hpp"
@@ -281,6 +282,144 @@ static void test_panda_memetic() {
     CHECK(ec.val == MoveItErrorCodes::NO_IK_SOLUTION && sol == home);
 }
 
+// the exact main overload (include/pick_ik/pick_ik_plugin.hpp:31-41): a custom IKCostFn is refused with a defined
+// status; an empty one and a context_state are accepted
+static void test_cost_function_and_context_state() {
+    PickIKPlugin plugin;
+    CHECK(plugin.initialize(make_rr_model_for_ik(), "group", "base", {"ee"}, 0.0));
+    Params p;
+    p.mode = "local";
+    plugin.setParams(p);
+    std::vector<double> const seed = {0.1, -0.1};
+    std::vector<double> sol;
+    MoveItErrorCodes ec;
+    compat::RobotState context;
+    int calls = 0;
+    compat::IKCostFn cost = [&](Pose const&, compat::RobotState const&, compat::JointModelGroup const*, std::vector<double> const&) {
+        ++calls;
+        return 0.0;
+    };
+    CHECK(!plugin.searchPositionIK({make_pose(3, 0, 0, 1, 0, 0, 0)}, seed, 0.05, {}, sol, compat::IKCallbackFn(), cost, ec,
+                                   KinematicsQueryOptions(), &context));
+    CHECK(ec.val == MoveItErrorCodes::NO_IK_SOLUTION && sol == seed && calls == 0);
+    CHECK(plugin.lastError().find("IKCostFn") != std::string::npos);
+    CHECK(plugin.searchPositionIK({make_pose(3, 0, 0, 1, 0, 0, 0)}, seed, 0.05, {}, sol, compat::IKCallbackFn(), compat::IKCostFn(), ec,
+                                  KinematicsQueryOptions(), &context));
+    CHECK(ec.val == MoveItErrorCodes::SUCCESS);
+    // one pose per tip frame
+    CHECK(!plugin.searchPositionIK({make_pose(3, 0, 0, 1, 0, 0, 0), make_pose(3, 0, 0, 1, 0, 0, 0)}, seed, 0.05, {}, sol,
+                                   compat::IKCallbackFn(), ec));
+}
+
+// species inside the engine (src/ik_memetic.cpp:315-370): the cheapest value over all species wins when they all run
+// to their end; the batch entry hands the costs back
+static void test_species_pick() {
+    PickIKPlugin plugin;
+    CHECK(plugin.initialize(make_panda_model(), "panda_arm", "panda_link0", {"panda_hand"}, 0.0));
+    std::vector<double> const home = {0.0, -M_PI_4, 0.0, -3.0 * M_PI_4, 0.0, M_PI_2, M_PI_4};
+    Pose const goal = make_pose(0.30689059, 0.0, 0.59028174, 0.0, 1.0, 0.0, 0.0);
+    std::vector<Pose> poses(32, goal);
+    std::vector<std::vector<double>> seeds(32, std::vector<double>(7, 0.0)), sols;
+    for (int b = 0; b < 32; ++b) seeds[b][1] = -0.1 - 0.02 * b, seeds[b][3] = -1.5;
+    std::vector<MoveItErrorCodes> codes;
+    std::vector<double> cost1, cost4, cost4all;
+    Params p;
+    p.memetic_max_generations = 40;
+    plugin.setParams(p);
+    CHECK(plugin.searchPositionIKBatch(poses, seeds, sols, codes, KinematicsQueryOptions(), &cost1) >= 28);
+    p.memetic_num_threads = 4;
+    plugin.setParams(p);
+    CHECK(plugin.searchPositionIKBatch(poses, seeds, sols, codes, KinematicsQueryOptions(), &cost4) >= 30);
+    p.memetic_stop_on_first_solution = false;
+    plugin.setParams(p);
+    long const solved_all = plugin.searchPositionIKBatch(poses, seeds, sols, codes, KinematicsQueryOptions(), &cost4all);
+    CHECK(solved_all >= 30 && cost1.size() == 32 && cost4all.size() == 32);
+    int lower = 0;
+    for (int b = 0; b < 32; ++b) {
+        if (codes[b].val != MoveItErrorCodes::SUCCESS) continue;
+        CHECK(cost4all[b] <= cost4[b]);  // every species ran on: the pick is the minimum over at least the same values
+        lower += cost4all[b] < cost4[b] ? 1 : 0;
+    }
+    CHECK(lower > 0);
+}
+
+// two tip frames on a tree (src/pick_ik_plugin.cpp:60-68, src/goal.cpp:80-89): one pose per tip
+static void test_two_tips() {
+    ChainModel m;
+    m.group_name = "both_arms";
+    m.model_frame = "base";
+    add_joint(m, "torso", "torso_link", PIK_JOINT_REVOLUTE, 0, 0, 0.4, 0, 0, 0, -1.5, 1.5, 1.0);
+    add_joint(m, "l1", "l1_link", PIK_JOINT_REVOLUTE, 0, 0.2, 0.3, 0.3, 0, 0, -2.0, 2.0, 1.5);
+    add_joint(m, "l2", "l2_link", PIK_JOINT_REVOLUTE, 0.3, 0, 0, 0, 0.5, 0, -2.2, 2.2, 1.5);
+    add_joint(m, "l_tool", "l_hand", PIK_JOINT_FIXED, 0.2, 0, 0, 0, 0, 0, 0, 0, 0);
+    add_joint(m, "r1", "r1_link", PIK_JOINT_REVOLUTE, 0, -0.2, 0.3, -0.3, 0, 0, -2.0, 2.0, 1.5);
+    add_joint(m, "r2", "r2_link", PIK_JOINT_REVOLUTE, 0.3, 0, 0, 0, 0.5, 0, -2.2, 2.2, 1.5);
+    add_joint(m, "r_tool", "r_hand", PIK_JOINT_FIXED, 0.2, 0, 0, 0, 0, 0, 0, 0, 0);
+    add_joint(m, "head", "head_link", PIK_JOINT_REVOLUTE, 0, 0, 0.5, 0, 0, 0, -1.0, 1.0, 1.0);  // not below a tip: unused
+    m.parent = {-1, 0, 1, 2, 0, 4, 5, 0};
+    PickIKPlugin plugin;
+    CHECK(plugin.initialize(m, "both_arms", "base", {"l_hand", "r_hand"}, 0.0));
+    CHECK(plugin.getJointNames().size() == 5 && plugin.getLinkNames().size() == 2);
+    // targets: FK of a known configuration, through the engine itself
+    pik_robot* robot = nullptr;
+    std::vector<pik_joint_desc> used(m.joints.begin(), m.joints.begin() + 7);
+    int32_t const parent[7] = {-1, 0, 1, 2, 0, 4, 5}, tips[2] = {3, 6};
+    CHECK(pik_robot_create_tree(used.data(), 7, parent, tips, 2, nullptr, nullptr, nullptr, &robot) == PIK_OK);
+    CHECK(pik_robot_num_variables(robot) == 5 && pik_robot_num_tips(robot) == 2);
+    pik_solver* solver = nullptr;
+    CHECK(pik_solver_create(robot, 0, nullptr, &solver) == PIK_OK);
+    pik_params pp;
+    pik_params_default(&pp);
+    double const q_goal[5] = {0.4, 0.7, -0.5, -0.6, 0.9};
+    double const seed5[5] = {0, 0, 0, 0, 0};
+    double const ident[14] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
+    double tip[14];
+    CHECK(pik_eval_cost(solver, &pp, 1, ident, seed5, 0, q_goal, nullptr, nullptr, tip, PIK_MEM_HOST) == PIK_OK);
+    std::vector<Pose> goals = {make_pose(tip[0], tip[1], tip[2], tip[3], tip[4], tip[5], tip[6]),
+                               make_pose(tip[7], tip[8], tip[9], tip[10], tip[11], tip[12], tip[13])};
+    std::vector<double> sol;
+    MoveItErrorCodes ec;
+    CHECK(plugin.searchPositionIK(goals, {0, 0, 0, 0, 0}, 1.0, {}, sol, compat::IKCallbackFn(), ec));
+    CHECK(ec.val == MoveItErrorCodes::SUCCESS && sol.size() == 5);
+    // the solution reaches BOTH goals
+    int32_t is_solution = 0;
+    double goal14[14];
+    std::memcpy(goal14, tip, sizeof(goal14));
+    CHECK(pik_eval_cost(solver, &pp, 1, goal14, seed5, 0, sol.data(), nullptr, &is_solution, nullptr, PIK_MEM_HOST) == PIK_OK);
+    CHECK(is_solution == 1);
+    // one pose only: refused
+    CHECK(!plugin.searchPositionIK(std::vector<Pose>{goals[0]}, {0, 0, 0, 0, 0}, 0.1, {}, sol, compat::IKCallbackFn(), ec));
+    pik_solver_destroy(solver);
+    pik_robot_destroy(robot);
+}
+
+// searchPositionIK is const and re-entrant (the reference serialises on its FK mutex only): concurrent callers with
+// the same inputs get the same answers as a lone caller
+static void test_concurrent_callers() {
+    PickIKPlugin plugin;
+    CHECK(plugin.initialize(make_panda_model(), "panda_arm", "panda_link0", {"panda_hand"}, 0.0));
+    Pose const goal = make_pose(0.30689059, 0.0, 0.59028174, 0.0, 1.0, 0.0, 0.0);
+    std::vector<std::vector<double>> guesses;
+    for (int k = 0; k < 6; ++k) guesses.push_back({0.05 * k, -0.3, 0.0, -1.5 - 0.1 * k, 0.0, 1.2, 0.3});
+    std::vector<std::vector<double>> alone(guesses.size());
+    for (size_t k = 0; k < guesses.size(); ++k) {
+        MoveItErrorCodes ec;
+        CHECK(plugin.searchPositionIK(goal, guesses[k], 5.0, alone[k], ec));
+    }
+    std::vector<std::vector<double>> together(guesses.size());
+    std::vector<int> ok(guesses.size(), 0);
+    std::vector<std::thread> threads;
+    for (size_t k = 0; k < guesses.size(); ++k)
+        threads.emplace_back([&, k] {
+            for (int rep = 0; rep < 3; ++rep) {
+                MoveItErrorCodes ec;
+                ok[k] = plugin.searchPositionIK(goal, guesses[k], 5.0, together[k], ec) ? 1 : 0;
+            }
+        });
+    for (auto& t : threads) t.join();
+    for (size_t k = 0; k < guesses.size(); ++k) CHECK(ok[k] == 1 && together[k] == alone[k]);
+}
+
 int main(int argc, char** argv) {
     bool cpu_only = false;
     std::string yaml = "pick_ik_b200/host/pick_ik_parameters.yaml";
@@ -299,6 +438,10 @@ int main(int argc, char** argv) {
         }
         test_rr_ik();
         test_panda_memetic();
+        test_cost_function_and_context_state();
+        test_species_pick();
+        test_two_tips();
+        test_concurrent_callers();
     }
     std::printf("%d checks, %d failures\n", g_checks, g_failures);
     return g_failures == 0 ? 0 : 1;

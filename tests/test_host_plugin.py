@@ -48,3 +48,41 @@ def test_plugin_solves_on_gpu():
     r = run()
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failures" in r.stdout
+
+
+MOVEIT_EXE = os.path.join(ROOT, "tests", "cpp", "_build", "test_moveit_plugin")
+
+
+def build_moveit():
+    from pick_ik_b200 import build as pik_build
+
+    lib = pik_build.build()
+    os.makedirs(os.path.dirname(MOVEIT_EXE), exist_ok=True)
+    srcs = [os.path.join(ROOT, "tests", "cpp", "test_moveit_plugin.cpp"),
+            os.path.join(ROOT, "pick_ik_b200", "host", "moveit", "pick_ik_b200_plugin.cpp"),
+            os.path.join(ROOT, "pick_ik_b200", "host", "pick_ik_plugin.cpp")]
+    libdir = os.path.dirname(lib)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "tests", "cpp", "mock_moveit"),
+                           "-o", MOVEIT_EXE] + srcs + ["-L" + libdir, "-lpik_b200", "-Wl,-rpath," + libdir, "-lpthread"])
+
+
+def test_real_moveit_translation_unit_compiles_against_the_api_mocks_and_registers():
+    """pick_ik_b200/host/moveit/pick_ik_b200_plugin.cpp: every `override` matches kinematics::KinematicsBase, the class
+    registers through PLUGINLIB_EXPORT_CLASS, initialize flattens a RobotModel; without MoveIt headers the translation
+    unit is empty."""
+    build_moveit()
+    r = subprocess.run([MOVEIT_EXE, "--cpu-only"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failures" in r.stdout
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only",
+                           os.path.join(ROOT, "pick_ik_b200", "host", "moveit", "pick_ik_b200_plugin.cpp")])
+    xml = open(os.path.join(ROOT, "pick_ik_b200", "host", "moveit", "pick_ik_b200_kinematics_description.xml")).read()
+    assert 'type="pick_ik_b200::MoveItPickIKPlugin"' in xml and 'base_class_type="kinematics::KinematicsBase"' in xml
+
+
+@pytest.mark.gpu
+def test_moveit_plugin_solves_two_tip_goal_on_gpu():
+    build_moveit()
+    r = subprocess.run([MOVEIT_EXE], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failures" in r.stdout
