@@ -163,11 +163,33 @@ int pik_robot_is_valid_configuration(const pik_robot* robot, const double* q);
  * joint_names, link_names (optional): capacity * PIK_URDF_NAME_BYTES chars each, one NUL-terminated name per
  * joint / per child link of that joint (the last link is the tip).
  * PIK_E_INVALID_ROBOT: malformed XML / tip not below base; PIK_E_UNSUPPORTED: floating, planar or mimic
- * joints on the chain.
+ * joints on the chain (pik_urdf_tree takes them); PIK_E_INVALID_ARGUMENT: a name longer than PIK_URDF_NAME_BYTES - 1
+ * (names are never truncated); PIK_E_OUT_OF_MEMORY.  No exception crosses the boundary.
  */
 #define PIK_URDF_NAME_BYTES 64
 int pik_urdf_chain(const char* urdf_xml, const char* base_link, const char* tip_link, pik_joint_desc* out,
                    int32_t capacity, int32_t* n_joints, char* joint_names, char* link_names);
+/*
+ * The general form, for pik_robot_create_tree: the joints between base_link and every one of the n_tips tip links
+ * (what get_active_variable_indices walks, src/robot.cpp:122-143), parents first and every branch contiguous
+ * (depth-first, children in document order), with
+ *   parent [capacity], tip_joint [n_tips], mimic_of / mimic_factor / mimic_offset [capacity]
+ * as pik_robot_create_tree takes them (<mimic joint multiplier offset>; a mimic joint whose master is not among
+ * these joints: PIK_E_UNSUPPORTED).  floating and planar joints are emitted with MoveIt's default bounds.
+ * Size query as above (capacity == 0, out == NULL).
+ */
+int pik_urdf_tree(const char* urdf_xml, const char* base_link, const char* const* tip_links, int32_t n_tips,
+                  pik_joint_desc* out, int32_t capacity, int32_t* n_joints, int32_t* parent, int32_t* tip_joint,
+                  int32_t* mimic_of, double* mimic_factor, double* mimic_offset, char* joint_names, char* link_names);
+/*
+ * SRDF planning group -> base link and tip links (the part of the JointModelGroup the plugin needs,
+ * src/pick_ik_plugin.cpp:42-49): the <chain base_link tip_link/> entries of <group name=GROUP>, sub-groups
+ * (<group name=.../> inside a group) included.  base_link: PIK_URDF_NAME_BYTES chars; tip_links: capacity *
+ * PIK_URDF_NAME_BYTES chars; *n_tips receives the number of chains (size query with capacity == 0).
+ * PIK_E_UNSUPPORTED: the group lists joints / links only, or its chains do not share one base link.
+ */
+int pik_srdf_group(const char* srdf_xml, const char* group, char* base_link, char* tip_links, int32_t capacity,
+                   int32_t* n_tips);
 
 /* stream: a cudaStream_t (or NULL for a stream owned by the solver) */
 int pik_solver_create(const pik_robot* robot, int32_t device, void* stream, pik_solver** out);

@@ -29,7 +29,7 @@ EXPORTS = [
     "pik_robot_is_valid_configuration", "pik_robot_chain_signature", "pik_random_configurations", "pik_solver_create", "pik_solver_destroy", "pik_solve_batch",
     "pik_solve_batch_async", "pik_solver_wait", "pik_solver_query", "pik_eval_cost", "pik_solver_synchronize", "pik_solver_get_stats", "pik_solver_last_error",
     "pik_device_count", "pik_host_alloc", "pik_host_free", "pik_measure_fp64_peak",
-    "pik_urdf_chain", "pik_comm_unique_id", "pik_comm_create", "pik_comm_destroy", "pik_comm_last_error", "pik_solve_batch_sharded",
+    "pik_urdf_chain", "pik_urdf_tree", "pik_srdf_group", "pik_comm_unique_id", "pik_comm_create", "pik_comm_destroy", "pik_comm_last_error", "pik_solve_batch_sharded",
     "pik_solve_batch_gather",
 ]
 COMM_ID_BYTES = 128
@@ -131,6 +131,9 @@ def lib() -> C.CDLL:
     L.pik_host_free.argtypes = [vp]
     L.pik_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.pik_urdf_chain.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp, C.c_int32, C.POINTER(C.c_int32), vp, vp]
+    L.pik_urdf_tree.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int32, vp, C.c_int32, C.POINTER(C.c_int32),
+                                vp, vp, vp, vp, vp, vp, vp]
+    L.pik_srdf_group.argtypes = [C.c_char_p, C.c_char_p, vp, vp, C.c_int32, C.POINTER(C.c_int32)]
     L.pik_comm_unique_id.argtypes = [vp]
     L.pik_comm_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.pik_comm_destroy.restype = None
@@ -368,6 +371,50 @@ def urdf_chain(urdf_xml: str, base_link: str, tip_link: str):
         raise PikError(rc, "pik_urdf_chain")
     raw = names.raw
     return desc, [raw[k * URDF_NAME_BYTES:(k + 1) * URDF_NAME_BYTES].split(b"\0")[0].decode() for k in range(n.value)]
+
+
+def _names(buf, n):
+    raw = buf.raw
+    return [raw[k * URDF_NAME_BYTES:(k + 1) * URDF_NAME_BYTES].split(b"\0")[0].decode() for k in range(n)]
+
+
+def urdf_tree(urdf_xml: str, base_link: str, tip_links):
+    """pik_urdf_tree: dict(desc, parent, tip_joint, mimic_of, mimic_factor, mimic_offset, joint_names, link_names) of the
+    joints between base_link and the tip links, parents first (the arguments of pik_robot_create_tree)."""
+    n = C.c_int32()
+    xml, base = urdf_xml.encode(), base_link.encode()
+    tips = (C.c_char_p * len(tip_links))(*[t.encode() for t in tip_links])
+    rc = lib().pik_urdf_tree(xml, base, tips, len(tip_links), None, 0, C.byref(n), None, None, None, None, None, None, None)
+    if rc != PIK_OK:
+        raise PikError(rc, "pik_urdf_tree")
+    k = n.value
+    desc = np.zeros(k, dtype=JOINT_DESC_DTYPE)
+    parent, mimic_of = np.zeros(k, dtype=np.int32), np.zeros(k, dtype=np.int32)
+    tip_joint = np.zeros(len(tip_links), dtype=np.int32)
+    factor, offset = np.zeros(k), np.zeros(k)
+    jn, ln = C.create_string_buffer(max(1, k) * URDF_NAME_BYTES), C.create_string_buffer(max(1, k) * URDF_NAME_BYTES)
+    vp = C.c_void_p
+    rc = lib().pik_urdf_tree(xml, base, tips, len(tip_links), desc.ctypes.data_as(vp), k, C.byref(n), parent.ctypes.data_as(vp),
+                             tip_joint.ctypes.data_as(vp), mimic_of.ctypes.data_as(vp), factor.ctypes.data_as(vp),
+                             offset.ctypes.data_as(vp), jn, ln)
+    if rc != PIK_OK:
+        raise PikError(rc, "pik_urdf_tree")
+    return dict(desc=desc, parent=parent, tip_joint=tip_joint, mimic_of=mimic_of, mimic_factor=factor, mimic_offset=offset,
+                joint_names=_names(jn, k), link_names=_names(ln, k))
+
+
+def srdf_group(srdf_xml: str, group: str):
+    """pik_srdf_group: (base_link, [tip_links]) of a planning group defined by <chain> entries."""
+    n = C.c_int32()
+    base = C.create_string_buffer(URDF_NAME_BYTES)
+    rc = lib().pik_srdf_group(srdf_xml.encode(), group.encode(), base, None, 0, C.byref(n))
+    if rc != PIK_OK:
+        raise PikError(rc, "pik_srdf_group")
+    tips = C.create_string_buffer(max(1, n.value) * URDF_NAME_BYTES)
+    rc = lib().pik_srdf_group(srdf_xml.encode(), group.encode(), base, tips, n.value, C.byref(n))
+    if rc != PIK_OK:
+        raise PikError(rc, "pik_srdf_group")
+    return base.raw.split(b"\0")[0].decode(), _names(tips, n.value)
 
 
 def comm_unique_id() -> bytes:

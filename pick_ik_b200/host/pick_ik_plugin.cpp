@@ -249,6 +249,45 @@ compat::ChainModel compat::chain_from_urdf(std::string const& urdf_xml, std::str
     return m;
 }
 
+compat::ChainModel compat::model_from_urdf_srdf(std::string const& urdf_xml, std::string const& srdf_xml,
+                                                std::string const& group_name, std::vector<std::string>& tip_frames) {
+    int32_t n_tips = 0;
+    char base[PIK_URDF_NAME_BYTES];
+    int rc = pik_srdf_group(srdf_xml.c_str(), group_name.c_str(), base, nullptr, 0, &n_tips);
+    if (rc != PIK_OK) throw std::invalid_argument(std::string("model_from_urdf_srdf: group ") + group_name + ": " + pik_status_string(rc));
+    std::vector<char> tips((size_t)n_tips * PIK_URDF_NAME_BYTES + 1);
+    rc = pik_srdf_group(srdf_xml.c_str(), group_name.c_str(), base, tips.data(), n_tips, &n_tips);
+    if (rc != PIK_OK) throw std::invalid_argument(std::string("model_from_urdf_srdf: ") + pik_status_string(rc));
+    tip_frames.clear();
+    std::vector<char const*> tip_ptrs;
+    for (int32_t t = 0; t < n_tips; ++t) {
+        tip_frames.emplace_back(tips.data() + (size_t)t * PIK_URDF_NAME_BYTES);
+        tip_ptrs.push_back(tips.data() + (size_t)t * PIK_URDF_NAME_BYTES);
+    }
+    int32_t n = 0;
+    rc = pik_urdf_tree(urdf_xml.c_str(), base, tip_ptrs.data(), n_tips, nullptr, 0, &n, nullptr, nullptr, nullptr, nullptr, nullptr,
+                       nullptr, nullptr);
+    if (rc != PIK_OK) throw std::invalid_argument(std::string("model_from_urdf_srdf: ") + pik_status_string(rc));
+    ChainModel m;
+    m.group_name = group_name;
+    m.model_frame = base;
+    m.joints.resize((size_t)n);
+    m.parent.resize((size_t)n);
+    m.mimic_of.resize((size_t)n);
+    m.mimic_factor.resize((size_t)n);
+    m.mimic_offset.resize((size_t)n);
+    std::vector<int32_t> tip_joint((size_t)n_tips);
+    std::vector<char> jn((size_t)n * PIK_URDF_NAME_BYTES + 1), ln((size_t)n * PIK_URDF_NAME_BYTES + 1);
+    rc = pik_urdf_tree(urdf_xml.c_str(), base, tip_ptrs.data(), n_tips, m.joints.data(), n, &n, m.parent.data(), tip_joint.data(),
+                       m.mimic_of.data(), m.mimic_factor.data(), m.mimic_offset.data(), jn.data(), ln.data());
+    if (rc != PIK_OK) throw std::invalid_argument(std::string("model_from_urdf_srdf: ") + pik_status_string(rc));
+    for (int32_t k = 0; k < n; ++k) {
+        m.joint_names.emplace_back(jn.data() + (size_t)k * PIK_URDF_NAME_BYTES);
+        m.link_names.emplace_back(ln.data() + (size_t)k * PIK_URDF_NAME_BYTES);
+    }
+    return m;
+}
+
 bool PickIKPlugin::initialize(compat::ChainModel const& model, std::string const& group_name,
                               std::string const& base_frame, std::vector<std::string> const& tip_frames,
                               double /*search_discretization*/, int device) {

@@ -78,6 +78,13 @@ struct ChainModel {
 ChainModel chain_from_urdf(std::string const& urdf_xml, std::string const& group_name, std::string const& base_link,
                            std::string const& tip_link);
 
+// URDF + SRDF -> the planning group's model: the group's <chain> entries give the base link and the tip links
+// (pik_srdf_group), the URDF the joints between them with mimic joints (pik_urdf_tree).  tip_frames receives the tip
+// links of the group (what a MoveIt configuration passes to initialize).  Throws std::invalid_argument like
+// chain_from_urdf.
+ChainModel model_from_urdf_srdf(std::string const& urdf_xml, std::string const& srdf_xml, std::string const& group_name,
+                                std::vector<std::string>& tip_frames);
+
 }  // namespace compat
 
 // pick_ik::Params (generated from src/pick_ik_parameters.yaml by generate_parameter_library): same member

@@ -399,6 +399,40 @@ def mimic_arm() -> RobotTree:
     return RobotTree("mimic_arm", j, [4])
 
 
+def tree_to_urdf(tree: RobotTree, base_link: str = "base"):
+    """The tree as a URDF document and the names of its tip links (links are named after their parent joints).  The
+    decimal literals are repr() round-trips, so pik_urdf_tree reproduces tree_arrays() bit for bit."""
+    def f(v):
+        return " ".join(repr(float(x)) for x in v)
+
+    kinds = {JOINT_FIXED: "fixed", JOINT_PRISMATIC: "prismatic", JOINT_FLOATING: "floating", JOINT_PLANAR: "planar"}
+    lines = ['<?xml version="1.0"?>', f'<robot name="{tree.name}">', f'  <link name="{base_link}"/>']
+    link_of = [f"{j.name}_link" for j in tree.joints]
+    for k, j in enumerate(tree.joints):
+        parent = base_link if j.parent < 0 else link_of[j.parent]
+        kind = kinds.get(j.type, "continuous" if j.continuous else "revolute")
+        lines.append(f'  <link name="{link_of[k]}"/>')
+        lines.append(f'  <joint name="{j.name}" type="{kind}">')
+        lines.append(f'    <parent link="{parent}"/>')
+        lines.append(f'    <child link="{link_of[k]}"/>')
+        lines.append(f'    <origin xyz="{f(j.xyz)}" rpy="{f(j.rpy)}"/>')
+        if j.type in (JOINT_REVOLUTE, JOINT_PRISMATIC):
+            lines.append(f'    <axis xyz="{f(j.axis)}"/>')
+            if j.continuous:
+                lines.append(f'    <limit effort="10" velocity="{float(j.velocity)!r}"/>')
+            else:
+                lines.append(f'    <limit effort="10" lower="{float(j.lower)!r}" upper="{float(j.upper)!r}" '
+                             f'velocity="{float(j.velocity)!r}"/>')
+        elif j.type in (JOINT_FLOATING, JOINT_PLANAR):
+            lines.append(f'    <limit effort="10" velocity="{float(j.velocity)!r}"/>')
+        if j.mimic_of >= 0:
+            lines.append(f'    <mimic joint="{tree.joints[j.mimic_of].name}" multiplier="{float(j.mimic_factor)!r}" '
+                         f'offset="{float(j.mimic_offset)!r}"/>')
+        lines.append("  </joint>")
+    lines.append("</robot>")
+    return "\n".join(lines) + "\n", [link_of[t] for t in tree.tip_joints]
+
+
 TREES = {"two_arm": two_arm, "three_tip": three_tip, "floating_arm": floating_arm, "planar_arm": planar_arm,
          "mimic_arm": mimic_arm}
 

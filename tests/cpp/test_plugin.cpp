@@ -175,6 +175,56 @@ static void test_chain_from_urdf() {
     CHECK(threw);
 }
 
+// URDF + SRDF -> planning-group model (pik_srdf_group + pik_urdf_tree): two chains off a common torso, a mimic finger
+static char const* kTwoArmUrdf =
+    "<robot name='two_arm'><link name='base'/><link name='torso_link'/><link name='l1_link'/><link name='l2_link'/>"
+    "<link name='l_hand'/><link name='r1_link'/><link name='r2_link'/><link name='r_hand'/><link name='head_link'/>"
+    "<joint name='torso' type='revolute'><parent link='base'/><child link='torso_link'/><origin xyz='0 0 0.4'/><axis xyz='0 0 1'/>"
+    "<limit lower='-1.5' upper='1.5' velocity='1' effort='1'/></joint>"
+    "<joint name='l1' type='revolute'><parent link='torso_link'/><child link='l1_link'/><origin xyz='0 0.2 0.3' rpy='0.3 0 0'/>"
+    "<axis xyz='0 0 1'/><limit lower='-2' upper='2' velocity='1.5' effort='1'/></joint>"
+    "<joint name='l2' type='revolute'><parent link='l1_link'/><child link='l2_link'/><origin xyz='0.3 0 0' rpy='0 0.5 0'/>"
+    "<axis xyz='0 0 1'/><limit lower='-2.2' upper='2.2' velocity='1.5' effort='1'/></joint>"
+    "<joint name='l_tool' type='fixed'><parent link='l2_link'/><child link='l_hand'/><origin xyz='0.2 0 0'/></joint>"
+    "<joint name='r1' type='revolute'><parent link='torso_link'/><child link='r1_link'/><origin xyz='0 -0.2 0.3' rpy='-0.3 0 0'/>"
+    "<axis xyz='0 0 1'/><limit lower='-2' upper='2' velocity='1.5' effort='1'/></joint>"
+    "<joint name='r2' type='revolute'><parent link='r1_link'/><child link='r2_link'/><origin xyz='0.3 0 0' rpy='0 0.5 0'/>"
+    "<axis xyz='0 0 1'/><limit lower='-2.2' upper='2.2' velocity='1.5' effort='1'/><mimic joint='l2' multiplier='-1' offset='0.1'/></joint>"
+    "<joint name='r_tool' type='fixed'><parent link='r2_link'/><child link='r_hand'/><origin xyz='0.2 0 0'/></joint>"
+    "<joint name='head' type='revolute'><parent link='torso_link'/><child link='head_link'/><origin xyz='0 0 0.5'/><axis xyz='0 0 1'/>"
+    "<limit lower='-1' upper='1' velocity='1' effort='1'/></joint></robot>";
+static char const* kTwoArmSrdf =
+    "<robot name='two_arm'><group name='left'><chain base_link='base' tip_link='l_hand'/></group>"
+    "<group name='right'><chain base_link='base' tip_link='r_hand'/></group>"
+    "<group name='both'><group name='left'/><group name='right'/></group></robot>";
+
+static void test_model_from_urdf_srdf(bool have_gpu) {
+    std::vector<std::string> tips;
+    auto const m = pick_ik_b200::compat::model_from_urdf_srdf(kTwoArmUrdf, kTwoArmSrdf, "both", tips);
+    CHECK(tips.size() == 2 && m.model_frame == "base" && m.joints.size() == 7);  // head is not below a tip
+    CHECK(m.parent.size() == 7 && m.parent[0] == -1 && m.mimic_of.size() == 7);
+    int mimics = 0;
+    for (size_t j = 0; j < m.joints.size(); ++j)
+        if (m.mimic_of[j] >= 0) {
+            ++mimics;
+            CHECK(m.joint_names[j] == "r2" && m.joint_names[(size_t)m.mimic_of[j]] == "l2" && m.mimic_factor[j] == -1.0 &&
+                  m.mimic_offset[j] == 0.1);
+        }
+    CHECK(mimics == 1);
+    bool threw = false;
+    try {
+        pick_ik_b200::compat::model_from_urdf_srdf(kTwoArmUrdf, kTwoArmSrdf, "no_such_group", tips);
+    } catch (std::invalid_argument const&) {
+        threw = true;
+    }
+    CHECK(threw);
+    if (!have_gpu) return;
+    PickIKPlugin plugin;
+    auto const model = pick_ik_b200::compat::model_from_urdf_srdf(kTwoArmUrdf, kTwoArmSrdf, "both", tips);
+    CHECK(plugin.initialize(model, "both", "base", tips, 0.0));
+    CHECK(plugin.getJointNames().size() == 4);  // torso, l1, l2, r1; r2 mimics l2
+}
+
 // tests/ik_tests.cpp:137-238 through the plugin, local mode, IkTestParams (:78-86)
 static void test_rr_ik() {
     PickIKPlugin plugin;
@@ -431,6 +481,7 @@ int main(int argc, char** argv) {
     test_params(yaml);
     test_initialize_errors(have_gpu);
     test_chain_from_urdf();
+    test_model_from_urdf_srdf(have_gpu && !cpu_only);
     if (!cpu_only) {
         if (!have_gpu) {
             std::printf("no CUDA device: the solve sections need one\n");

@@ -1,4 +1,5 @@
 """pik_urdf_chain (host-only C-ABI): URDF -> chain table with urdfdom / MoveIt semantics."""
+import ctypes as C
 import math
 
 import numpy as np
@@ -98,3 +99,88 @@ def test_errors():
     assert e.value.status == -2
     desc, _ = capi.urdf_chain(URDF, "tool", "tool")  # empty chain
     assert len(desc) == 0
+
+
+def test_urdf_tree_round_trips_the_tree_fixtures():
+    """pik_urdf_tree: several tips, mimic joints, parents-first order -- the arguments of pik_robot_create_tree."""
+    for name in ("two_arm", "three_tip", "mimic_arm"):
+        tree = robots.TREES[name]()
+        xml, tips = robots.tree_to_urdf(tree)
+        got = capi.urdf_tree(xml, "base", tips)
+        desc, parent, tip_joint, mimic_of, factor, offset = tree.tree_arrays()
+        # the reader walks the tree depth-first (children in document order): map its joints back by name
+        index = {j.name: k for k, j in enumerate(tree.joints)}
+        order = [index[n] for n in got["joint_names"]]
+        assert sorted(order) == list(range(len(tree.joints))), name
+        back = {old: new for new, old in enumerate(order)}
+        for new, old in enumerate(order):
+            for f in desc.dtype.names:
+                if f == "axis" and desc[old]["type"] == 0:
+                    continue  # a fixed joint has no <axis>
+                np.testing.assert_array_equal(got["desc"][new][f], desc[old][f], err_msg=f"{name} {got['joint_names'][new]} {f}")
+            assert got["parent"][new] == (back[parent[old]] if parent[old] >= 0 else -1)
+            assert got["mimic_of"][new] == (back[mimic_of[old]] if mimic_of[old] >= 0 else -1)
+            if mimic_of[old] >= 0:
+                assert (got["mimic_factor"][new], got["mimic_offset"][new]) == (factor[old], offset[old])
+        assert [order[t] for t in got["tip_joint"]] == list(tip_joint)
+        # and the robot built from it has the variables of the fixture (joint order within a depth may differ from the
+        # fixture's only where branches interleave, which these fixtures do not do for their moving joints)
+        h = C.c_void_p()
+        vp = C.c_void_p
+        rc = capi.lib().pik_robot_create_tree(got["desc"].ctypes.data_as(vp), len(got["desc"]), got["parent"].ctypes.data_as(vp),
+                                              got["tip_joint"].ctypes.data_as(vp), len(tips), got["mimic_of"].ctypes.data_as(vp),
+                                              got["mimic_factor"].ctypes.data_as(vp), got["mimic_offset"].ctypes.data_as(vp), C.byref(h))
+        assert rc == 0
+        assert capi.lib().pik_robot_num_variables(h) == tree.num_variables
+        assert capi.lib().pik_robot_num_tips(h) == tree.num_tips
+        capi.lib().pik_robot_destroy(h)
+
+
+def test_urdf_tree_floating_planar_and_errors():
+    for name in ("floating_arm", "planar_arm"):
+        tree = robots.TREES[name]()
+        xml, tips = robots.tree_to_urdf(tree)
+        got = capi.urdf_tree(xml, "base", tips)
+        assert got["desc"][0]["type"] == (3 if name == "floating_arm" else 4) and got["desc"][0]["bounded"] == 0
+        # the single-tip chain reader has no multi-variable joints
+        with pytest.raises(capi.PikError) as e:
+            capi.urdf_chain(xml, "base", tips[0])
+        assert e.value.status == -7
+    xml, tips = robots.tree_to_urdf(robots.mimic_arm())
+    with pytest.raises(capi.PikError) as e:
+        capi.urdf_chain(xml, "base", tips[0])  # a mimic joint on the chain: use pik_urdf_tree
+    assert e.value.status == -7
+    with pytest.raises(capi.PikError) as e:
+        capi.urdf_tree(xml, "base", ["no_such_link"])
+    assert e.value.status == -2
+    # a name that does not fit PIK_URDF_NAME_BYTES is an error, not a truncation
+    long_name = "j" * 80
+    doc = (f'<robot name="r"><link name="a"/><link name="b"/><joint name="{long_name}" type="revolute"><parent link="a"/>'
+           '<child link="b"/><axis xyz="0 0 1"/><limit lower="-1" upper="1" velocity="1" effort="1"/></joint></robot>')
+    with pytest.raises(capi.PikError) as e:
+        capi.urdf_chain(doc, "a", "b")
+    assert e.value.status == -1
+
+
+def test_srdf_group_chains():
+    srdf = """<?xml version="1.0"?>
+    <robot name="two_arm">
+      <!-- planning groups -->
+      <group name="left_arm"><chain base_link="base" tip_link="l_tool_link"/></group>
+      <group name="right_arm"><chain base_link="base" tip_link="r_tool_link"/></group>
+      <group name="both_arms"><group name="left_arm"/><group name="right_arm"/></group>
+      <group name="by_joints"><joint name="torso"/></group>
+      <end_effector name="l" parent_link="l_tool_link" group="left_arm"/>
+    </robot>"""
+    assert capi.srdf_group(srdf, "left_arm") == ("base", ["l_tool_link"])
+    base, tips = capi.srdf_group(srdf, "both_arms")
+    assert base == "base" and sorted(tips) == ["l_tool_link", "r_tool_link"]
+    for group, status in (("by_joints", -7), ("no_such_group", -2)):
+        with pytest.raises(capi.PikError) as e:
+            capi.srdf_group(srdf, group)
+        assert e.value.status == status
+    # SRDF group -> URDF tree -> robot: the stand-alone replacement of RobotModel + JointModelGroup
+    tree = robots.two_arm()
+    xml, _ = robots.tree_to_urdf(tree)
+    got = capi.urdf_tree(xml, base, tips)
+    assert len(got["desc"]) == len(tree.joints) and len(got["tip_joint"]) == 2
