@@ -583,6 +583,120 @@ __device__ __forceinline__ int gd_elite_wide(const WarpSmem& W, int L, int lane,
     return steps;
 }
 
+// gd_elite_wide for chains whose n finite-difference pairs fill the L lanes of an elite exactly (n a multiple of L, L >=
+// 4: the Fetch's 8 variables on 8 or 4 lanes): the accepted point of step s - 1, which gd_elite_wide evaluates beside the
+// finite differences of step s, would cost a whole extra sub-round there, so it moves into the line-search round of step
+// s, onto the row lanes (line_search_rows3).  step() then learns the cost of its point one round later: the gradient
+// and the line search of step s are computed before the termination test of step s - 1 is known and are discarded when
+// it fires (the previous gradient, which gradientDescent returns, is kept aside in registers until then).  Same
+// results as the serial loop: every evaluation is a full chain walk of its configuration.
+template <class S>
+__device__ __forceinline__ int gd_elite_wide_deferred(const WarpSmem& W, int L, int lane, bool valid, const double* g7,
+                                                      const double* sd, double& best_cost_out) {
+    const int n = c_rb.n;
+    const int c = lane / L, gl = lane % L;
+    const bool leader = gl == 0;
+    double* q = W.q + c;
+    double* g = W.g + c;
+    double* best = W.best + c;
+    double* sc = W.sc + c;
+    double* csM = W.cs + c;       // finite-difference costs, then sin/cos of q - g
+    double* csP = W.cs + c + 8;   // sin/cos of q + g (L >= 4: at most 8 groups per warp, columns 8..15 are free)
+    const double h = c_pr.step_size;
+    double local_cost = 0.0, best_cost = 0.0, previous_cost = 0.0;
+    int it = 0, steps = 0;
+    bool act_l = valid && leader;  // the group still runs (leader's copy)
+    bool first = true;
+    for (;;) {
+        // fin: this round only settles the last step (its cost is all that is missing)
+        const unsigned st = __shfl_sync(kFull, (act_l ? 1u : 0u) | ((!first && it + 1 >= c_pr.gd_max_iters) ? 2u : 0u), c * L);
+        const bool act = (st & 1u) != 0 && valid;
+        const bool fin = (st & 2u) != 0;
+        if (!__any_sync(kFull, act)) break;
+        for (int j = gl; j < n; j += L) {
+            if (act) {
+                double sj, cj;
+                joint_sincos<S>(j, q[j * kS], sj, cj);
+                sc[(2 * j) * kS] = sj;
+                sc[(2 * j + 1) * kS] = cj;
+            }
+        }
+        __syncwarp();
+        // round A: the n finite-difference pairs, one per lane
+        const bool spec = act && !fin;
+        for (int k = gl; k < n; k += L) {
+            if (spec) {
+                const CostPair cp = pair_costs_from_origin<S>(kPairFd, k, q, nullptr, sc, g7, sd);
+                csM[(2 * k) * kS] = cp.m;
+                csM[(2 * k + 1) * kS] = cp.p;
+            }
+        }
+        __syncwarp();
+        // the gradient of this step (ik_gradient.cpp:42-54), speculative; the previous one is kept in registers
+        double g_old[4] = {0.0, 0.0, 0.0, 0.0};
+        if (spec) {
+            double sum = h;
+            for (int i = 0; i < n; ++i) sum = sum + fabs(csM[(2 * i + 1) * kS] - csM[(2 * i) * kS]);
+            const double f = 1.0 / sum * h;
+            int slot = 0;
+            for (int j = gl; j < n; j += L, ++slot) {
+                const double gj = (csM[(2 * j + 1) * kS] - csM[(2 * j) * kS]) * f;
+                if (slot < 4) g_old[slot] = g[j * kS];
+                g[j * kS] = gj;
+            }
+        }
+        __syncwarp();
+        // round B: the line search of this step and the cost of its starting point, on the row lanes
+        const double cost = line_search_rows3<S>(L, gl, spec, act, q, g, sc, csM, csP, g7, sd);
+        const double p1 = __shfl_sync(kFull, cost, c * L), p3 = __shfl_sync(kFull, cost, c * L + 1);
+        const double cur = __shfl_sync(kFull, cost, c * L + 2);
+        bool improved = false;
+        if (act && leader) {
+            if (first) {
+                local_cost = best_cost = cur;  // GradientIk::from
+                if (c_pr.gd_max_iters <= 0) act_l = false;
+            } else {
+                // the tail of step(): the accepted point's cost, best update (ik_gradient.cpp:88-93), then the
+                // loop control of gradientDescent (ik_memetic.cpp:75-86)
+                local_cost = cur;
+                if (local_cost < best_cost) {
+                    improved = true;
+                    best_cost = local_cost;
+                }
+                ++steps;
+                if (fabs(local_cost - previous_cost) <= c_pr.min_cost_delta) {
+                    act_l = false;
+                } else {
+                    previous_cost = local_cost;
+                    ++it;
+                    if (it >= c_pr.gd_max_iters) act_l = false;
+                }
+            }
+        }
+        first = false;
+        const unsigned ctl = __shfl_sync(kFull, (act_l ? 1u : 0u) | (improved ? 2u : 0u), c * L);
+        const bool go = (ctl & 1u) != 0 && valid;
+        if (act) {
+            int slot = 0;
+            for (int j = gl; j < n; j += L, ++slot) {
+                if (ctl & 2u) best[j * kS] = q[j * kS];
+                if (!go && spec && slot < 4) g[j * kS] = g_old[slot];  // the step ended here: its gradient stands
+            }
+        }
+        // the always-accepted step (ik_gradient.cpp:67-85), one joint per lane
+        if (go) {
+            const double p2 = (p1 + p3) * 0.5;
+            const double cost_diff = (p3 - p1) * 0.5;
+            double joint_diff = p2 / cost_diff;
+            if (!(fabs(joint_diff) <= 0x1.fffffffffffffp+1023)) joint_diff = 0.0;  // !isfinite
+            for (int j = gl; j < n; j += L) q[j * kS] = clamp_to_limits(j, q[j * kS] - g[j * kS] * joint_diff);
+        }
+        __syncwarp();
+    }
+    best_cost_out = best_cost;
+    return steps;
+}
+
 // -----------------------------------------------------------------------------------------------
 // One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for PW problems per warp.
 // -----------------------------------------------------------------------------------------------
@@ -809,7 +923,11 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                 printf("pik wide gd phases: sincos %lld  roundA %lld  control %lld  roundB %lld  accept %lld\n", ph[0], ph[1],
                        ph[2], ph[3], ph[4]);
 #else
-            const int steps = gd_elite_wide<S>(W, L, lane, valid, W.goal + (7 * c_rb.n_tips) * (valid ? k : 0), sd, best_cost);
+            // (n a multiple of L: the accepted point would cost the finite-difference round an extra sub-round)
+            const bool deferred = !S::kTree && L >= 4 && n % L == 0 && n <= 4 * L && (c_pr.lockstep & 4) == 0;
+            const int steps = deferred
+                                  ? gd_elite_wide_deferred<S>(W, L, lane, valid, W.goal + (7 * c_rb.n_tips) * (valid ? k : 0), sd, best_cost)
+                                  : gd_elite_wide<S>(W, L, lane, valid, W.goal + (7 * c_rb.n_tips) * (valid ? k : 0), sd, best_cost);
 #endif
             if (leader) gd_steps = steps;
         }
