@@ -397,8 +397,14 @@ int orc_robot_build_tree(const orc_joint_desc* joints, int n_joints, const int32
         orc_step* st = &out->steps[ns];
         const int up = fold_origins(joints, parent, j, st->R, st->t);
         st->parent = up >= 0 ? step_of[up] : -1;
-        memcpy(st->axis, jd->axis, sizeof(st->axis));
+        /* unit axis: moveit_core RevoluteJointModel::setAxis / PrismaticJointModel::setAxis normalise */
         double x = jd->axis[0], y = jd->axis[1], z = jd->axis[2];
+        const double a2 = x * x + y * y + z * z;
+        if (fabs(a2 - 1.0) > 1.0e-14 && a2 > 0.0) {  /* an axis that is unit to rounding is kept as given */
+            const double nrm = sqrt(a2);
+            x /= nrm; y /= nrm; z /= nrm;
+        }
+        st->axis[0] = x; st->axis[1] = y; st->axis[2] = z;
         st->axis_sq[0] = x * x; st->axis_sq[1] = y * y; st->axis_sq[2] = z * z;
         st->axis_sq[3] = x * y; st->axis_sq[4] = x * z; st->axis_sq[5] = y * z;
         st->sign = 1.0;

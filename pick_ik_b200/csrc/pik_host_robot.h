@@ -98,7 +98,14 @@ inline int build_dev_robot_tree(const pik_joint_desc* joints, int n_joints, cons
         out->parent[ns] = up >= 0 ? step_of[up] : -1;
         if (up >= 0 && step_of[up] < 0) return PIK_E_INVALID_ROBOT;
         if (out->parent[ns] != ns - 1) simple = false;
-        const double x = jd.axis[0], y = jd.axis[1], z = jd.axis[2];
+        // unit axis (RevoluteJointModel / PrismaticJointModel::setAxis normalise theirs); pik_robot_create admits
+        // |axis|^2 within 1e-6 of 1
+        double x = jd.axis[0], y = jd.axis[1], z = jd.axis[2];
+        const double a2 = x * x + y * y + z * z;
+        if (std::fabs(a2 - 1.0) > 1.0e-14 && a2 > 0.0) {  /* an axis that is unit to rounding is kept as given */
+            const double nrm = std::sqrt(a2);
+            x /= nrm; y /= nrm; z /= nrm;
+        }
         out->axis[ns][0] = x; out->axis[ns][1] = y; out->axis[ns][2] = z;
         out->axis_sq[ns][0] = x * x; out->axis_sq[ns][1] = y * y; out->axis_sq[ns][2] = z * z;
         out->axis_sq[ns][3] = x * y; out->axis_sq[ns][4] = x * z; out->axis_sq[ns][5] = y * z;

@@ -759,8 +759,11 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     const int max_gens = persistent ? c_pr.max_generations - gen : 1;
     // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
     // GD step (below): warps that run the same code at the same time share their instruction-cache fills.
-    const bool lockstep = L == 1 && (c_pr.lockstep & 1) != 0;
-    const bool lockstep_rep = L == 1 && (c_pr.lockstep & 2) != 0;
+    // Every warp of the CTA executes the same number of these barriers before it reaches the claim barrier again
+    // (idle warps run them empty below; nobody leaves the CTA early); a persistent launch, whose warps run different
+    // numbers of generations, takes none.
+    const bool lockstep = L == 1 && !persistent && (c_pr.lockstep & 1) != 0;
+    const bool lockstep_rep = L == 1 && !persistent && (c_pr.lockstep & 2) != 0;
     const int pw_carve = S::kWide ? wide_problems_per_warp_max(E) : PW;
     const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, pw_carve, c_rb.n_tips), n, P, pw_carve, c_rb.n_tips);
     const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;

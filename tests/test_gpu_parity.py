@@ -254,3 +254,19 @@ def test_sub_batches_reproduce_the_undivided_solve(solvers, monkeypatch):
             monkeypatch.setenv("PIK_SUB_BATCHES", k)
             check_solve(solver.solve_batch(gp, goal, seed, first_problem_index=77), ref, f"sub-batches {k} {kw}")
             assert solver.stats().solved == (ref["error_code"] == 1).sum()
+
+
+def test_axis_within_tolerance_is_normalised():
+    """pik_robot_create admits |axis|^2 within 1e-6 of 1; the table is built from the unit axis
+    (RevoluteJointModel::setAxis normalises), in the library and in the oracle alike."""
+    desc = robots.skew6().joint_desc().copy()
+    for j in range(len(desc)):
+        desc[j]["axis"] = tuple(np.array(desc[j]["axis"]) * (1.0 + 4.0e-7))
+    orobot = orc.build_robot(desc)
+    solver = capi.Solver(capi.Robot(desc))
+    op, gp = both_params(mode="local")
+    B = 300
+    seed = random_configs(orobot, B, 3)
+    goal = np.stack([orc.pose_from_fk(orobot, s + 0.05) for s in seed])
+    check_solve(solver.solve_batch(gp, goal, seed), orc.solve_batch(orobot, op, goal, seed), "scaled axes")
+    solver.close()

@@ -95,3 +95,18 @@ def test_goal_cost_formulas():
     assert math.isclose(center, exp_center, rel_tol=1e-13)
     assert math.isclose(avoid, exp_avoid, rel_tol=1e-13) and avoid > 0
     assert math.isclose(mind, exp_mind, rel_tol=1e-13)
+
+
+def test_axis_is_normalised():
+    """moveit_core's setAxis normalises the joint axis; a description whose axes are 4e-7 too long must give an
+    orthonormal tip rotation (and the pose of the unit-axis robot to rounding)."""
+    desc = robots.skew6().joint_desc().copy()
+    unit = orc.build_robot(desc)
+    for j in range(len(desc)):
+        desc[j]["axis"] = tuple(np.array(desc[j]["axis"]) * (1.0 + 4.0e-7))
+    scaled = orc.build_robot(desc)
+    q = np.array([0.3, -0.7, 1.1, 0.4, -1.3, 0.9])
+    R, t = orc.fk(scaled, q)
+    R0, t0 = orc.fk(unit, q)
+    assert np.abs(R @ R.T - np.eye(3)).max() < 1e-14
+    assert np.abs(R - R0).max() < 1e-14 and np.abs(t - t0).max() < 1e-14
