@@ -59,6 +59,10 @@ struct WarpSmem {
     int* flag;     // [32]
     int* ctl;      // [4]
     uint16_t* perm;  // [next power of two >= P] positions being sorted (robots with unbounded variables)
+    // side-by-side reproduce (robots without unbounded variables; aliases perm):
+    double* rtf;   // [64] per problem slot: fitness of the E best so far, then of the worst
+    int* rti;      // [64] ... and their positions
+    int* grp;      // [64] per problem slot: mating pool size, [32 + slot]: next child
 };
 
 // fit aliases the sc rows (dead once the elite searches are done) when the population fits there
@@ -73,7 +77,9 @@ __host__ __device__ inline int pow2_at_least(int v) {
 __host__ __device__ inline size_t warp_smem_bytes(int n, int P, int PW, int T) {
     size_t d = (size_t)5 * n * kS + (fit_in_sc(n, P) ? 0 : (size_t)P) + (size_t)PW * 7 * T + 3 * 32;
     size_t i = 32 + 33 + 32 + 32 + 4;
-    return ((d * 8 + i * 4 + (size_t)pow2_at_least(P) * 2) + 15) & ~size_t(15);
+    size_t tail = (size_t)pow2_at_least(P) * 2;  // perm, or rtf + rti + grp
+    if (tail < 64 * 8 + 128 * 4) tail = 64 * 8 + 128 * 4;
+    return ((d * 8 + i * 4 + 4 + tail) + 15) & ~size_t(15);
 }
 
 __device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P, int PW, int T) {
@@ -99,7 +105,11 @@ __device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int n, int P
     W.pidx = ip; ip += 32;
     W.flag = ip; ip += 32;
     W.ctl = ip; ip += 4;
+    if ((reinterpret_cast<uintptr_t>(ip) & 7) != 0) ++ip;
     W.perm = reinterpret_cast<uint16_t*>(ip);
+    W.rtf = reinterpret_cast<double*>(ip);
+    W.rti = ip + 128;
+    W.grp = ip + 192;
     return W;
 }
 
@@ -840,8 +850,14 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     if (base >= n_active) {
         if (lockstep)
             for (int step = 0; step < c_pr.gd_max_iters; ++step) __syncthreads();
-        if (lockstep_rep)
-            for (int k = 0; k < PW; ++k) __syncthreads();
+        if (lockstep_rep) {
+            if (PW > 1 && !c_rb.any_unbounded && (c_pr.lockstep & 8) == 0) {
+                while (__syncthreads_or(0)) {
+                }
+            } else {
+                for (int k = 0; k < PW; ++k) __syncthreads();
+            }
+        }
     } else {
     if (lane < PW) {
         const int64_t idx = base + lane;
@@ -954,39 +970,78 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     // ---- per problem: reproduce, sortPopulation, best update
     const double inv_n = 1.0 / (double)n;
     int n_problems = 0;
-    for (int k = 0; k < PW; ++k) {
-        if (lockstep_rep) __syncthreads();  // re-align the CTA's warps at every problem (instruction-cache sharing)
-        const int b = W.pidx[k];
-        if (b < 0) continue;
-        ++n_problems;
-        const int iter = sb.meta[b].iter;
-        const double* src = pop_ptr(sb, iter & 1, b, n, P);
-        double* dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
-        const uint16_t* ord_in = order_ptr(sb, iter & 1, b, P);
-        uint16_t* ord_out = order_ptr(sb, (iter & 1) ^ 1, b, P);
-        const double* sd = sb.seed + (size_t)problem_of(sb, b) * sb.seed_stride;
-        const double* g7 = W.goal + (7 * c_rb.n_tips) * k;
-        const int c0 = k * E;  // first elite column of this problem
-        const uint32_t rng_problem = (uint32_t)(sb.first_problem_index + problem_of(sb, b));
-        const uint32_t rng_species = species_of(sb, b);
-        if (lane < E) {
-            W.fit[lane] = W.efit[c0 + lane];
-            W.pool[lane] = lane;
+    // Robots without unbounded variables need only the E best and the worst of a generation, which are kept as the
+    // children are committed: the G = PW problems of the warp reproduce side by side, 32 / G lanes each (a child
+    // that removes a parent costs its problem the rest of a window of 32 / G children instead of 32).  Otherwise
+    // (whole order needed, or one problem per warp) one problem at a time over all 32 lanes.
+    const int G = (PW > 1 && !c_rb.any_unbounded && (c_pr.lockstep & 8) == 0) ? PW : 1;
+    const int LG = 32 / G;
+    for (int k0 = 0; k0 < PW; k0 += G) {
+        if (lockstep_rep && G == 1) __syncthreads();  // re-align the CTA's warps at every problem (instruction-cache sharing)
+        const bool in_group = lane / LG < G;  // (32 / G lanes per problem: E = 5 leaves lanes 30 and 31 out)
+        const int kk = in_group ? k0 + lane / LG : k0;  // this lane's problem slot
+        const int gl = lane % LG;
+        const int b = in_group ? W.pidx[kk] : -1;
+        const int c0 = kk * E;  // first elite column of the problem
+        const int t0 = kk * (E + 1);
+        int iter = 0;
+        const double* src = nullptr;
+        double* dst = nullptr;
+        const uint16_t* ord_in = nullptr;
+        const double* sd = nullptr;
+        uint32_t rng_problem = 0, rng_species = 0;
+        if (b >= 0) {
+            iter = sb.meta[b].iter;
+            src = pop_ptr(sb, iter & 1, b, n, P);
+            dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
+            ord_in = order_ptr(sb, iter & 1, b, P);
+            sd = sb.seed + (size_t)problem_of(sb, b) * sb.seed_stride;
+            rng_problem = (uint32_t)(sb.first_problem_index + problem_of(sb, b));
+            rng_species = species_of(sb, b);
         }
-        if (lane == 0) W.ctl[0] = E;
+        const double* g7 = W.goal + (7 * c_rb.n_tips) * kk;
+        if (gl < E && in_group) {
+            const double fe = W.efit[c0 + gl];
+            W.pool[c0 + gl] = gl;
+            if (G == 1) {
+                W.fit[gl] = fe;
+            } else {
+                // running order of the E best (the elites to begin with) and the worst, key (fitness, position)
+                int rank = 0;
+                for (int e = 0; e < E; ++e)
+                    if (key_less(W.efit[c0 + e], e, fe, gl)) ++rank;
+                W.rtf[t0 + rank] = fe;
+                W.rti[t0 + rank] = gl;
+                if (rank == E - 1) {
+                    W.rtf[t0 + E] = fe;
+                    W.rti[t0 + E] = gl;
+                }
+            }
+        }
+        if (gl == 0 && in_group) {
+            W.grp[kk] = E;                  // mating pool size
+            W.grp[32 + kk] = b >= 0 ? E : P;  // next child
+        }
         __syncwarp();
 
         // reproduce (src/ik_memetic.cpp:119-190).  A child that beats a parent removes it from the mating
         // pool, which changes the parent draws of every later child: a window is committed up to the first
         // such child and the walk resumes after it.  Each child's random stream is keyed by (generation,
         // child), so its draws do not depend on the history.
-        int s = E;
         double* col = W.q + lane;
         if (dbg) t_rep -= clock64();
-        while (s < P) {
-            const int i = s + lane;
+        for (;;) {
+            const int s = in_group ? W.grp[32 + kk] : P;
+            const int i = s + gl;
             const bool actv = i < P;
-            const int ps = W.ctl[0];
+            const bool any = __any_sync(kFull, actv);
+            if (lockstep_rep && G > 1) {
+                if (!__syncthreads_or(any)) break;  // the CTA's warps walk their windows in step
+                if (!any) continue;
+            } else if (!any) {
+                break;
+            }
+            const int ps = W.grp[kk];
             double f = 0.0;
             int ia = 0, ib = 0;
             bool removes = false;
@@ -1007,8 +1062,8 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                     const uint32_t idxA = uniform_int_words(sb, iw, (uint32_t)ps);
                     uint32_t idxB = idxA;
                     while (idxB == idxA && ps > 1) idxB = uniform_int_words(sb, iw, (uint32_t)ps);
-                    ia = W.pool[idxA];
-                    ib = W.pool[idxB];
+                    ia = W.pool[c0 + idxA];
+                    ib = W.pool[c0 + idxB];
                     const int ca = c0 + ia, cb = c0 + ib;
                     const double extinction = 0.5 * (W.eext[ca] + W.eext[cb]);
                     const double mutation_prob = extinction * (1.0 - inv_n) + inv_n;
@@ -1046,39 +1101,86 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                 dst[(size_t)(2 * n) * P + slot] = f;
                 if (ps > 0) removes = f < W.efit[c0 + ia] || f < W.efit[c0 + ib];
             }
-            const unsigned mask = __ballot_sync(kFull, removes);
-            if (mask) {
-                const int l = __ffs(mask) - 1;
-                const double fl = __shfl_sync(kFull, f, l);
-                const int a = __shfl_sync(kFull, ia, l), bb = __shfl_sync(kFull, ib, l);
-                if (actv && lane <= l) W.fit[i] = f;
-                if (lane == 0) {
+            const unsigned ballot = __ballot_sync(kFull, removes);
+            const unsigned gmask = LG == 32 ? ballot : (ballot >> (lane - gl)) & ((1u << LG) - 1u);  // this problem's lanes
+            const int l = gmask ? __ffs(gmask) - 1 : LG - 1;  // last lane of the group whose child is committed
+            const int from = (lane - gl + l) & 31;
+            const double fl = __shfl_sync(kFull, f, from);
+            const int a = __shfl_sync(kFull, ia, from), bb = __shfl_sync(kFull, ib, from);
+            const bool commit = actv && gl <= l;
+            if (gl == 0 && actv) {
+                if (gmask) {
                     int p2 = ps;
                     // parents are referenced by identity; A first, then B (ik_memetic.cpp:170-177)
                     for (int which = 0; which < 2; ++which) {
                         const int target = which == 0 ? a : bb;
                         if (fl < W.efit[c0 + target]) {
                             for (int x = 0; x < p2; ++x)
-                                if (W.pool[x] == target) {
-                                    for (int y = x; y + 1 < p2; ++y) W.pool[y] = W.pool[y + 1];
+                                if (W.pool[c0 + x] == target) {
+                                    for (int y = x; y + 1 < p2; ++y) W.pool[c0 + y] = W.pool[c0 + y + 1];
                                     --p2;
                                     break;
                                 }
                         }
                     }
-                    W.ctl[0] = p2;
+                    W.grp[kk] = p2;
                 }
-                s += l + 1;
+                W.grp[32 + kk] = s + l + 1;
+            }
+            if (G == 1) {
+                if (commit) W.fit[i] = f;
             } else {
-                if (actv) W.fit[i] = f;
-                s += 32;
+                // the committed children that enter the E best or become the worst, in position order
+                const bool enters = commit && (key_less(f, i, W.rtf[t0 + E - 1], W.rti[t0 + E - 1]) ||
+                                               key_less(W.rtf[t0 + E], W.rti[t0 + E], f, i));
+                const unsigned eb = __ballot_sync(kFull, enters);
+                if (eb) {
+                    W.fit[lane] = f;  // (the sc rows: free during reproduce)
+                    __syncwarp();
+                    unsigned em = LG == 32 ? eb : (eb >> (lane - gl)) & ((1u << LG) - 1u);
+                    if (gl == 0) {
+                        while (em) {
+                            const int x = __ffs(em) - 1;
+                            em &= em - 1;
+                            const double fx = W.fit[lane + x];
+                            const int ix = s + x;
+                            if (key_less(W.rtf[t0 + E], W.rti[t0 + E], fx, ix)) {
+                                W.rtf[t0 + E] = fx;
+                                W.rti[t0 + E] = ix;
+                            }
+                            int r = E;
+                            while (r > 0 && key_less(fx, ix, W.rtf[t0 + r - 1], W.rti[t0 + r - 1])) --r;
+                            if (r < E) {
+                                for (int y = E - 1; y > r; --y) {
+                                    W.rtf[t0 + y] = W.rtf[t0 + y - 1];
+                                    W.rti[t0 + y] = W.rti[t0 + y - 1];
+                                }
+                                W.rtf[t0 + r] = fx;
+                                W.rti[t0 + r] = ix;
+                            }
+                        }
+                    }
+                }
             }
             __syncwarp();
         }
-
         if (dbg) t_rep += clock64();
+
+      for (int k = k0; k < k0 + G; ++k) {
+        const int b = W.pidx[k];
+        if (b < 0) continue;
+        ++n_problems;
+        const int iter = sb.meta[b].iter;
+        double* dst = pop_ptr(sb, (iter & 1) ^ 1, b, n, P);
+        const uint16_t* ord_in = order_ptr(sb, iter & 1, b, P);
+        uint16_t* ord_out = order_ptr(sb, (iter & 1) ^ 1, b, P);
         // sortPopulation (src/ik_memetic.cpp:200-209) under the total order (fitness, position), NaN last.
-        if (c_rb.any_unbounded) {
+        if (G > 1) {
+            // the running order kept while the children were committed
+            for (int i = lane; i < P; i += 32) ord_out[i] = ord_in[i];
+            for (int r = lane; r <= E; r += 32) W.top[r] = W.rti[k * (E + 1) + r];
+            __syncwarp();
+        } else if (c_rb.any_unbounded) {
             // whole order needed: the previous occupant of every position may seed a random individual.  Bitonic
             // sort of the positions (padded to a power of two; padding sorts last) in shared memory: the key is a
             // total order, so any sorting network gives the permutation of the reference's stable sort.
@@ -1140,6 +1242,8 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                 pi = mi;
             }
             __syncwarp();
+        }
+        if (!c_rb.any_unbounded) {
             if (lane == 0) {
                 // bring the E best to the front of the slot-index row with swaps
                 for (int r = 0; r < E; ++r) W.pool[r] = W.top[r];
@@ -1157,11 +1261,12 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
             __syncwarp();
         }
         // computeExtinctions (ik_memetic.cpp:57-64); only the next generation's parents are ever read
-        const double f0 = W.fit[W.top[0]];
-        const double fmax = W.fit[W.top[E]];
+        auto top_fitness = [&](int r) { return G > 1 ? W.rtf[k * (E + 1) + r] : W.fit[W.top[r]]; };
+        const double f0 = top_fitness(0);
+        const double fmax = top_fitness(E);
         if (lane < E) {
             const double grading = (double)lane / (double)(P - 1);
-            dst[(size_t)(2 * n + 1) * P + ord_out[lane]] = (W.fit[W.top[lane]] + f0 * (grading - 1.0)) / fmax;
+            dst[(size_t)(2 * n + 1) * P + ord_out[lane]] = (top_fitness(lane) + f0 * (grading - 1.0)) / fmax;
         }
         double* hdr = sb.hdr + (size_t)b * (n + 2);
         if (f0 < hdr[n]) {  // best_ = best_curr_, ik_memetic.cpp:206-208
@@ -1172,6 +1277,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
         }
         if (lane == 0) W.f0s[k] = f0;
         __syncwarp();
+      }
     }
 
     if (dbg) t_sort = clock64();
