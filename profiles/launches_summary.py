@@ -4,6 +4,7 @@ command (one step = one 65 536-pose batch) the generation kernels' share of the 
 usage: python profiles/launches_summary.py gpurun_out/r02_launches.csv [traffic.json]"""
 import csv
 import json
+import re
 import sys
 from collections import defaultdict
 
@@ -12,7 +13,11 @@ def short(name):
     for key in ("memetic_generation_kernel", "memetic_init_kernel", "gd_local_kernel", "eval_cost_kernel", "species_pick_kernel",
                 "pack_results_kernel", "sm_discover_kernel", "fp64_peak_kernel"):
         if key in name:
-            wide = "wide" if ("Lb1ELb1E" in name or ", (bool)1, (int)2" in name) else "throughput"
+            # the Wide template flag: StaticSpec<n, kinds, tip, WIDE, ...>, PatternSpec<o, t, WIDE>, TreeSpec<WIDE>, GenericSpecW
+            m = (re.search(r"StaticSpec<\d+, \d+, \w+, (\w+)", name) or re.search(r"PatternSpec<\d+, \d+, (\w+)", name)
+                 or re.search(r"TreeSpec<(\w+)", name))
+            is_wide = (m and m.group(1) in ("1", "true", "(bool)1")) or "Lb1ELb1E" in name or "GenericSpec" in name
+            wide = "wide" if is_wide else "throughput"
             return key + (" [" + wide + "]" if key == "memetic_generation_kernel" else "")
     return "(library) " + name[:60]
 
