@@ -270,3 +270,31 @@ def test_axis_within_tolerance_is_normalised():
     goal = np.stack([orc.pose_from_fk(orobot, s + 0.05) for s in seed])
     check_solve(solver.solve_batch(gp, goal, seed), orc.solve_batch(orobot, op, goal, seed), "scaled axes")
     solver.close()
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("panda", dict(memetic_population_size=128)),
+    ("ur5", dict(memetic_population_size=48, memetic_elite_size=5, memetic_max_generations=40)),
+    ("skew6", dict(memetic_population_size=30, memetic_elite_size=3, memetic_max_generations=40)),
+])
+def test_reproduce_side_by_side_equals_one_at_a_time(solvers, name, kw, monkeypatch):
+    """The throughput mapping lets the problems of a warp reproduce side by side (32 / PW lanes each, running
+    E best + worst); PIK_LOCKSTEP_MASK bit 3 selects the one-problem-at-a-time form (windows of 32, fitness array).
+    Same bits, a batch large enough for multi-round launches, with and without the CTA-wide round barrier."""
+    chain, orobot, solver = solvers(name)
+    B = 6000
+    goal = orc.make_targets(orobot, B)
+    seed = np.array(robots.PANDA_HOME) if name == "panda" else random_configs(orobot, 1, 9)[0]
+    gp = capi.default_params(mode="global", **kw)
+    monkeypatch.setenv("PIK_LOCKSTEP_MASK", "11")
+    ref = solver.solve_batch(gp, goal, seed)
+    for mask in ("3", "1", "0"):
+        monkeypatch.setenv("PIK_LOCKSTEP_MASK", mask)
+        got = solver.solve_batch(gp, goal, seed)
+        for key in ("solution", "error_code", "cost", "iterations"):
+            np.testing.assert_array_equal(got[key], ref[key], err_msg=f"{name} mask {mask} {key}")
+    # and the one-at-a-time form against the oracle on a slice
+    op = orc.default_params(mode="global", **kw)
+    oref = orc.solve_batch(orobot, op, goal[:48], seed)
+    for key in ("solution", "error_code", "cost", "iterations"):
+        np.testing.assert_array_equal(ref[key][:48], oref[key], err_msg=f"{name} oracle {key}")
