@@ -630,8 +630,17 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
     sb.stats = static_cast<unsigned long long*>(s->d_stats.ptr);
     GenerationPlan plan;
     std::memset(&plan, 0, sizeof(plan));
-    const size_t n_counters = (size_t)pr.max_generations + 2;
-    const size_t n_sched = ((size_t)pr.max_generations + 1) * ((size_t)s->sm_count + 2);
+    // Launches of the throughput flavour may pass part of their list on (memetic_generation_kernel): a problem then
+    // lags behind the launch index, by at most the number of launches allowed to do so, and the solve gets that
+    // many launches more.  Species that may terminate one another advance strictly one generation per launch.
+    int defer_launches = 12;
+    if (const char* env = std::getenv("PIK_DEFER_LAUNCHES")) defer_launches = std::atoi(env);
+    if (defer_launches < 0 || !global || trace_each_generation() || (S > 1 && params->memetic_stop_on_first_solution)) defer_launches = 0;
+    if (defer_launches > pr.max_generations) defer_launches = pr.max_generations;
+    pr.defer_launches = defer_launches;
+    const int n_launches = pr.max_generations + defer_launches;
+    const size_t n_counters = (size_t)n_launches + 2;
+    const size_t n_sched = ((size_t)n_launches + 1) * ((size_t)s->sm_count + 2);
     const int64_t slice_problems = (B + K - 1) / K;  // problems per sub-batch (the last one may be shorter)
     if (global) {
         const size_t F = 2 * (size_t)n + 2;
@@ -657,6 +666,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
         pr.wide_capacity_lanes = plan.wide_capacity_lanes;
         pr.wide_units_max = plan.wide_units_max;
         pr.persistent_units_max = plan.persistent_units_max;
+        pr.wave_ctas = plan.wave_ctas;
         std::memcpy(pr.sm_dense, s->sm_dense, sizeof(pr.sm_dense));
     }
 
@@ -719,7 +729,7 @@ int enqueue_solve(pik_solver* s, const pik_params* params, int64_t B, int64_t fi
                 PIK_CUDA(s, launch_memetic_init(sk, s->spec, n, T, P, pr.E, w));
                 s->stats.kernel_launches += 1;
                 if (K == 1) PIK_CUDA(s, cudaEventRecord(s->ev2, st));
-                const int n_gens = plan.first_launch_runs_all ? 1 : pr.max_generations;
+                const int n_gens = plan.first_launch_runs_all ? 1 : n_launches;
                 for (int gen = 0; gen < n_gens; ++gen) {
                     if (trace) PIK_CUDA(s, cudaEventRecord(s->ev2, st));
                     if (plan.use_throughput) {

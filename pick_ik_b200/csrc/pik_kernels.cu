@@ -744,17 +744,27 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
                                                                       int gen) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_claim[4];
-    const int n_active = sb.counters[gen];
-    if (n_active <= 0) return;
+    const int n_listed = sb.counters[gen];
+    if (n_listed <= 0) return;
     const int n = c_rb.n, P = c_pr.P, E = c_pr.E;
-    const int L = lanes_for(n_active, E, c_pr.lanes_max, c_pr.wide_capacity_lanes, c_pr.wide_units_max);
+    const int L = lanes_for(n_listed, E, c_pr.lanes_max, c_pr.wide_capacity_lanes, c_pr.wide_units_max);
     if ((L > 1) != S::kWide) return;
     const int PW = 32 / (E * L);
     const int list_in = gen & 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    const int units = (n_active + PW - 1) / PW;
     const int nsm = c_pr.sm_count;
+    // Whole waves only: a throughput launch whose list is longer than what the resident CTAs hold at a time processes
+    // a whole number of such waves and passes the rest of the list on to the next launch untouched (problems are
+    // independent and carry their own generation count, so a launch is a scheduling step, not a generation: the
+    // part-filled last round of a launch runs at a fraction of the throughput of a full one).  The entries passed on
+    // are copied before anything else, so they lead the next list and are processed by the next launch.
+    int n_active = n_listed;
+    if (!S::kWide && gen < c_pr.defer_launches) {
+        const int wave = (int)gridDim.x * wpb * PW;
+        if ((int)gridDim.x == c_pr.wave_ctas && n_listed > wave) n_active = (n_listed / wave) * wave;
+    }
+    const int units = (n_active + PW - 1) / PW;
     const int sigma = c_pr.sm_dense[sm_id() & (kSmDenseSize - 1)];
     int* qhead = sb.sched + (size_t)gen * (size_t)(nsm + 2);  // [nsm] queue heads, CTAs that have left, units taken
     // Units are dealt to the queues in chunks: one unit at a time for the throughput flavour (every SM the same number
@@ -766,7 +776,8 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     const int n_chunks = (units + chunk - 1) / chunk;
     const int rot = sb.sm_rotation % nsm;
     const bool persistent = S::kWide && PW == 1 && units <= c_pr.persistent_units_max;  // (0 for species in lockstep)
-    const int max_gens = persistent ? c_pr.max_generations - gen : 1;
+    // (with launches that pass problems on, an upper bound: a problem leaves when ITS generation count is up)
+    const int max_gens = persistent ? (c_pr.defer_launches > 0 ? c_pr.max_generations : c_pr.max_generations - gen) : 1;
     // Throughput mode keeps the warps of a CTA in step through the GD phase with one block barrier per
     // GD step (below): warps that run the same code at the same time share their instruction-cache fills.
     // Every warp of the CTA executes the same number of these barriers before it reaches the claim barrier again
@@ -778,6 +789,19 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memeti
     const WarpSmem W = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(n, P, pw_carve, c_rb.n_tips), n, P, pw_carve, c_rb.n_tips);
     const int32_t* act_in = sb.active + (size_t)list_in * (size_t)sb.B;
     int32_t* act_out = sb.active + (size_t)(list_in ^ 1) * (size_t)sb.B;
+    if (n_active < n_listed) {
+        const int rest = n_listed - n_active;
+        const int per = (rest + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int lo = n_active + (int)blockIdx.x * per;
+        const int hi = lo + per < n_listed ? lo + per : n_listed;
+        if (lo < hi) {
+            if (threadIdx.x == 0) s_claim[0] = atomicAdd(&sb.counters[gen + 1], hi - lo);
+            __syncthreads();
+            const int at = s_claim[0];
+            for (int i = lo + (int)threadIdx.x; i < hi; i += (int)blockDim.x) act_out[at + (i - lo)] = act_in[i];
+            __syncthreads();  // s_claim is rewritten by the first claim
+        }
+    }
     bool worked = false, sweeping = false;
   for (;;) {
     if (warp == 0) {
@@ -1496,7 +1520,9 @@ GenerationPlan plan_generations(int n, int T, int P, int E, int64_t n_sub, int s
     // the per-SM queues, in as many rounds as it takes
     const int64_t per_block_t = (int64_t)t.problems_per_warp * t.warps;
     int64_t blocks_t = (n_sub + per_block_t - 1) / per_block_t;
-    if (blocks_t > (int64_t)2 * sm_count) blocks_t = (int64_t)2 * sm_count;
+    g.wave_ctas = 2 * sm_count;
+    if (const char* env = std::getenv("PIK_WAVE_CTAS")) g.wave_ctas = std::atoi(env) > 0 ? std::atoi(env) : g.wave_ctas;  // (tests)
+    if (blocks_t > (int64_t)g.wave_ctas) blocks_t = (int64_t)g.wave_ctas;
     g.blocks_t = (unsigned)blocks_t;
     g.lanes_max = memetic_max_lanes_per_elite(E);
     // largest power of two the doubling of lanes_for can reach

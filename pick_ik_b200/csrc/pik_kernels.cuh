@@ -50,7 +50,7 @@ struct GenerationPlan {
     unsigned blocks_t, blocks_w;
     int threads_t, threads_w;
     size_t smem_t, smem_w;
-    int lanes_max, wide_units_max, persistent_units_max;
+    int lanes_max, wide_units_max, persistent_units_max, wave_ctas;
     long long wide_capacity_lanes;
     bool use_throughput, use_wide, first_launch_runs_all;
 };

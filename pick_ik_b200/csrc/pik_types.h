@@ -85,6 +85,9 @@ struct DevParams {
     int wide_units_max;          // warps a wide launch provides (grid * warps per CTA)
     int persistent_units_max;    // a wide launch with one problem per warp and at most this many problems keeps
                                  // every problem for all its remaining generations (0: never)
+    int wave_ctas;               // the resident CTAs of a throughput launch (its grid, when the batch fills them)
+    int defer_launches;          // throughput launches 0 .. defer_launches - 1 process whole waves of resident CTAs only
+                                 // and pass the rest of their list on untouched (0: every launch processes its list)
     unsigned short sm_dense[kSmDenseSize];  // %smid -> 0 .. sm_count - 1 (%smid has holes where SMs are fused off)
 };
 

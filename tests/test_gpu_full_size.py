@@ -73,7 +73,8 @@ def test_panda_65536_memetic_pop128():
     ok = check_properties(solver, params, goal, home, res, 0.98)
     st = solver.stats()
     assert st.solved == ok.sum() and st.problems == B
-    assert st.generation_launches <= 100 and res["iterations"].max() <= 100
+    # (100 generations + the launches that may pass part of their list on: PIK_DEFER_LAUNCHES, 12)
+    assert st.generation_launches <= 112 and res["iterations"].max() <= 100
     picks = np.random.default_rng(0).choice(B, 96, replace=False)
     picks = np.concatenate([picks, np.flatnonzero(~ok)[:4]])  # a few that ran all 100 generations too
     spot_check(orc.build_robot(chain.joint_desc()), orc.default_params(**kw), goal, home, res, 0, picks)

@@ -298,3 +298,36 @@ def test_reproduce_side_by_side_equals_one_at_a_time(solvers, name, kw, monkeypa
     oref = orc.solve_batch(orobot, op, goal[:48], seed)
     for key in ("solution", "error_code", "cost", "iterations"):
         np.testing.assert_array_equal(ref[key][:48], oref[key], err_msg=f"{name} oracle {key}")
+
+
+@pytest.mark.parametrize("kw,B", [
+    (dict(memetic_population_size=16, memetic_max_generations=30), 1500),
+    # nothing converges: every problem runs all its generations, many of them a launch or more late
+    (dict(memetic_population_size=8, memetic_max_generations=9, position_threshold=1e-9, orientation_threshold=1e-9), 700),
+    (dict(memetic_population_size=12, memetic_max_generations=14, memetic_num_threads=2,
+          memetic_stop_on_first_solution=0), 400),
+])
+def test_whole_wave_launches(solvers, kw, B, monkeypatch):
+    """A throughput launch processes whole waves of its resident CTAs and passes the rest of its list on to the next
+    launch, so a problem's generation lags behind the launch index (PIK_WAVE_CTAS shrinks the wave so that batches
+    of test size take that path; PIK_DEFER_LAUNCHES=0 turns it off).  Same bits as the oracle either way."""
+    chain, orobot, solver = solvers("panda")
+    goal = orc.make_targets(orobot, B)
+    seed = np.array(robots.PANDA_HOME)
+    op, gp = both_params(mode="global", **kw)
+    ref = orc.solve_batch(orobot, op, goal, seed, first_problem_index=5)
+    monkeypatch.setenv("PIK_WIDE_WARPS_PER_SM", "0")  # throughput mapping throughout
+    for ctas, defer in (("3", None), ("1", "40"), ("2", "0")):
+        monkeypatch.setenv("PIK_WAVE_CTAS", ctas)
+        if defer is None:
+            monkeypatch.delenv("PIK_DEFER_LAUNCHES", raising=False)
+        else:
+            monkeypatch.setenv("PIK_DEFER_LAUNCHES", defer)
+        check_solve(solver.solve_batch(gp, goal, seed, first_problem_index=5), ref, f"wave of {ctas} CTAs, defer {defer}")
+        st = solver.stats()
+        assert st.problems == B and st.solved == (ref["error_code"] == 1).sum()
+    # default wide mapping behind the whole-wave launches
+    monkeypatch.delenv("PIK_WIDE_WARPS_PER_SM")
+    monkeypatch.setenv("PIK_WAVE_CTAS", "2")
+    monkeypatch.delenv("PIK_DEFER_LAUNCHES", raising=False)
+    check_solve(solver.solve_batch(gp, goal, seed, first_problem_index=5), ref, "wave of 2 CTAs, wide tail")
