@@ -474,43 +474,49 @@ def run_ours(args):
         assert lo.item() == hi.item(), "ranks disagree on the gathered results"
     assert mm.item() == 0, "%d spot-checked problems differ from the CPU oracle" % int(mm.item())
 
-    # ---- two batches in flight (extra figure; N = 1)
+    # ---- several batches in flight (extra figure; N = 1)
     pipelined = None
     if world == 1 and not args.no_pipelined:
-        s2 = torch.cuda.Stream(device=dev)
-        solver2 = capi.Solver(robot, device=local_rank, stream=s2.cuda_stream)
-        outs2 = [torch.empty((B, n), dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
-                 torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev)]
+        M = max(2, args.in_flight)
+        outs1 = [d_sol, d_err, d_cost, d_its]
+        pairs = [(solver, outs1)]
+        streams = []
+        for _ in range(M - 1):
+            sx = torch.cuda.Stream(device=dev)
+            streams.append(sx)
+            pairs.append((capi.Solver(robot, device=local_rank, stream=sx.cuda_stream),
+                          [torch.empty((B, n), dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+                           torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev)]))
 
         def launch(sv, outs):
             sv.solve_batch_async_ptr(params, B, first, d_goal.data_ptr(), d_seed.data_ptr(), 0, outs[0].data_ptr(),
                                      outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), capi.MEM_DEVICE)
 
-        outs1 = [d_sol, d_err, d_cost, d_its]
-        pairs = [(solver, outs1), (solver2, outs2)]
-        n_batches = 2 * max(2, args.steps)
-        launch(*pairs[0])
-        launch(*pairs[1])  # warm-up of the second solver's buffers
+        n_batches = M * max(2, args.steps)
+        for pr in pairs:  # warm-up of the solvers' buffers
+            launch(*pr)
         for sv, _ in pairs:
             sv.wait()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        launch(*pairs[0])
-        launch(*pairs[1])
-        for k in range(2, n_batches):
-            sv, outs = pairs[k % 2]
+        for pr in pairs:
+            launch(*pr)
+        for k in range(M, n_batches):
+            sv, outs = pairs[k % M]
             sv.wait()
             launch(sv, outs)
         for sv, _ in pairs:
             sv.wait()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        assert int((outs2[1] == 1).sum().item()) == solved and int((d_err == 1).sum().item()) == solved
-        pipelined = {"value": n_batches * B / dt, "unit": UNIT, "batches_in_flight": 2, "batches": n_batches,
+        for _, outs in pairs:
+            assert int((outs[1] == 1).sum().item()) == solved
+        pipelined = {"value": n_batches * B / dt, "unit": UNIT, "batches_in_flight": M, "batches": n_batches,
                      "ms_per_batch": 1e3 * dt / n_batches,
-                     "how": "two solvers on two streams sharing one constant table, pik_solve_batch_async / "
-                            "pik_solver_wait, device-resident buffers, wall clock over %d batches" % n_batches}
-        solver2.close()
+                     "how": "%d solvers on %d streams sharing one constant table, pik_solve_batch_async / "
+                            "pik_solver_wait, device-resident buffers, wall clock over %d batches" % (M, M, n_batches)}
+        for sv, _ in pairs[1:]:
+            sv.close()
 
     if rank == 0:
         n_evals_gd = 2 * n + 3
@@ -592,6 +598,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight of the extra `pipelined` figure")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
