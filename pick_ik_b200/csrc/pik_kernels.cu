@@ -14,11 +14,16 @@
 //     batch has drained so far that a launch is bound by the serial path of a generation, L lanes per elite
 //     (wide mapping, gd_elite_wide): the finite-difference pairs and the accepted point of the previous step
 //     in one round, the two line-search points in a second;
-//   * reproduction: the warp walks each problem's children in windows of 32 (one child per lane); the
-//     sequential mating-pool semantics of the reference are kept by committing a window only up to the
-//     first child that removes a parent and restarting after it with the shrunken pool;
-//   * the sort permutes a slot-index row, never the individuals (top-E selection by warp reductions;
-//     a full rank computation only for robots with unbounded variables, which need the whole order).
+//   * reproduction: children are made in windows, one child per lane; the sequential mating-pool semantics of
+//     the reference are kept by committing a window only up to the first child that removes a parent and
+//     restarting after it with the shrunken pool.  One problem per warp: windows of 32; PW > 1 problems per
+//     warp: side by side, 32 / PW lanes each, so that a removal throws away at most 32 / PW - 1 children;
+//   * the sort permutes a slot-index row, never the individuals (the E best and the worst: a running list kept
+//     while children are committed, or warp reductions over the fitness array; a full sort only for robots with
+//     unbounded variables, which need the whole order).
+// Scheduling.  Grids of resident CTAs take warp-units from one queue per SM; a launch is a scheduling step, not a
+// generation: problems carry their own generation count, and a throughput launch processes whole waves of its
+// resident CTAs only, passing the rest of its list on (see memetic_generation_kernel).
 // All arithmetic is binary64 with --fmad=false (see pik_device.cuh) and is bit-identical to
 // oracle/pik_oracle.c whatever the mapping.
 #include "pik_kernels.cuh"
