@@ -41,7 +41,8 @@ namespace pik {
 namespace {
 
 constexpr int kWarpsPerBlock = 4;       // every kernel but the throughput-mode generation launches
-constexpr int kWarpsPerBlockBulk = 8;   // throughput-mode generation launches: 8 warps in step (see `lockstep`)
+constexpr int kWarpsPerBlockBulk = 16;  // throughput-mode generation launches: ONE CTA per SM, its 16 warps in step (see
+                                        // `lockstep`; two CTAs of 8 warps: +3 % per wave, four of 4: +11 %)
 constexpr int kThreads = 32 * kWarpsPerBlock;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -715,12 +716,12 @@ __device__ __forceinline__ int gd_elite_wide_deferred(const WarpSmem& W, int L, 
 // -----------------------------------------------------------------------------------------------
 // One generation of ik_memetic_impl (src/ik_memetic.cpp:228-269) for PW problems per warp.
 // -----------------------------------------------------------------------------------------------
-// Register budgets: the throughput flavour (and the generic kernel, which serves both modes) runs 2 CTAs of
-// 8 warps per SM at 128 registers; the wide flavour (several lanes per elite) 3 CTAs of 4 warps at 168 registers
+// Register budgets: the throughput flavour (and the generic kernel, which serves both modes) runs 1 CTA of
+// 16 warps per SM at 128 registers; the wide flavour (several lanes per elite) 3 CTAs of 4 warps at 168 registers
 // (no spills: a lone warp pays the full latency of every local-memory access).
 //
 // Launch policy, evaluated on the device: the host enqueues, for every generation g, one launch of the throughput
-// flavour and one of the wide flavour -- each a grid of RESIDENT CTAs (2 resp. 3 per SM) -- and never reads a count
+// flavour and one of the wide flavour -- each a grid of RESIDENT CTAs (1 resp. 3 per SM) -- and never reads a count
 // back.  Each launch reads the size of generation g's active list, derives the lane mapping from it (lanes_for, the
 // function the host used to call) and returns at once unless the mapping is its own.
 //
@@ -745,7 +746,7 @@ __device__ __forceinline__ unsigned sm_id() {
 }
 
 template <class S>
-__global__ void __launch_bounds__(S::kWide ? 128 : 256, S::kWide ? 3 : 2) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
+__global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::kWide ? 3 : 1) memetic_generation_kernel(const __grid_constant__ SolveBuffers sb,
                                                                       int gen) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_claim[4];
@@ -1508,8 +1509,8 @@ MemeticShape memetic_shape(int n, int T, int P, int E, int lanes_per_elite) {
     s.warps = L == 1 ? kWarpsPerBlockBulk : kWarpsPerBlock;
     // the wide flavour carves its shared memory for the largest number of problems per warp it may be given
     const int pw_carve = L == 1 ? s.problems_per_warp : wide_problems_per_warp_max(E);
-    // a large population may not leave room for 8 warps' worth of shared memory
-    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, pw_carve, T) > 112 * 1024) --s.warps;
+    // a large population may not leave room for 16 (resp. 4) warps' worth of shared memory
+    while (s.warps > 1 && s.warps * warp_smem_bytes(n, P, pw_carve, T) > (L == 1 ? 200 : 112) * 1024) --s.warps;
     s.threads = 32 * s.warps;
     s.smem = s.warps * warp_smem_bytes(n, P, pw_carve, T);
     return s;
@@ -1521,11 +1522,11 @@ GenerationPlan plan_generations(int n, int T, int P, int E, int64_t n_sub, int s
     const MemeticShape t = memetic_shape(n, T, P, E, 1);
     g.threads_t = t.threads;
     g.smem_t = t.smem;
-    // grids of resident CTAs (2 per SM for the throughput flavour, 3 for the wide one): the CTAs claim their work from
-    // the per-SM queues, in as many rounds as it takes
-    const int64_t per_block_t = (int64_t)t.problems_per_warp * t.warps;
-    int64_t blocks_t = (n_sub + per_block_t - 1) / per_block_t;
-    g.wave_ctas = 2 * sm_count;
+    // grids of resident CTAs (1 per SM for the throughput flavour, 3 for the wide one): the CTAs claim their work from
+    // the per-SM queues, in as many rounds as it takes.  The units are dealt over all the SMs, so a batch of less than
+    // a wave still gets a CTA on every SM it has a unit for (whose surplus warps idle).
+    int64_t blocks_t = (n_sub + t.problems_per_warp - 1) / t.problems_per_warp;
+    g.wave_ctas = sm_count;
     if (const char* env = std::getenv("PIK_WAVE_CTAS")) g.wave_ctas = std::atoi(env) > 0 ? std::atoi(env) : g.wave_ctas;  // (tests)
     if (blocks_t > (int64_t)g.wave_ctas) blocks_t = (int64_t)g.wave_ctas;
     g.blocks_t = (unsigned)blocks_t;
