@@ -692,6 +692,7 @@ __device__ __forceinline__ int gd_elite_wide_deferred(const WarpSmem& W, int L, 
         first = false;
         const unsigned ctl = __shfl_sync(kFull, (act_l ? 1u : 0u) | (improved ? 2u : 0u), c * L);
         const bool go = (ctl & 1u) != 0 && valid;
+        __syncwarp();  // the row lanes have read q and g (line_search_rows3)
         if (act) {
             int slot = 0;
             for (int j = gl; j < n; j += L, ++slot) {
@@ -737,6 +738,17 @@ __device__ __forceinline__ int gd_elite_wide_deferred(const WarpSmem& W, int L, 
 // A wide launch with one problem per warp and at most persistent_units_max problems keeps every problem for all
 // its remaining generations: problems are independent, so the tail of the batch needs no global step between
 // generations; the launches enqueued behind it find an empty list.
+// Block barriers: the lanes of a warp reconverge first (bar.sync is an aligned barrier: every thread of a warp must
+// execute it together, which code that has just left a divergent region does not guarantee by itself).
+__device__ __forceinline__ void block_barrier() {
+    __syncwarp();
+    __syncthreads();
+}
+__device__ __forceinline__ int block_barrier_or(int predicate) {
+    __syncwarp();
+    return __syncthreads_or(predicate);
+}
+
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 __device__ __forceinline__ unsigned sm_id() {
@@ -802,10 +814,10 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
         const int hi = lo + per < n_listed ? lo + per : n_listed;
         if (lo < hi) {
             if (threadIdx.x == 0) s_claim[0] = atomicAdd(&sb.counters[gen + 1], hi - lo);
-            __syncthreads();
+            block_barrier();
             const int at = s_claim[0];
             for (int i = lo + (int)threadIdx.x; i < hi; i += (int)blockDim.x) act_out[at + (i - lo)] = act_in[i];
-            __syncthreads();  // s_claim is rewritten by the first claim
+            block_barrier();  // s_claim is rewritten by the first claim
         }
     }
     bool worked = false, sweeping = false;
@@ -854,13 +866,13 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
             s_claim[2] = got_n;
         }
     }
-    __syncthreads();
+    block_barrier();
     const int claim_q = s_claim[0], claim_e = s_claim[1], claim_n = s_claim[2];
     if (claim_n == 0) {
         if (sweeping) return;
         if (threadIdx.x == 0)
             s_claim[3] = (atomicAdd(&qhead[nsm], 1) == (int)gridDim.x - 1 && ld_volatile(&qhead[nsm + 1]) < n_chunks * chunk) ? 1 : 0;
-        __syncthreads();
+        block_barrier();
         if (!s_claim[3]) return;
         sweeping = true;
         continue;
@@ -877,17 +889,10 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
         const int64_t unit = ((int64_t)(e / chunk) * nsm + tq) * chunk + e % chunk;
         if (unit < units) base = unit * PW;
     }
-    if (base >= n_active) {
-        if (lockstep)
-            for (int step = 0; step < c_pr.gd_max_iters; ++step) __syncthreads();
-        if (lockstep_rep) {
-            if (PW > 1 && !c_rb.any_unbounded && (c_pr.lockstep & 8) == 0) {
-                while (__syncthreads_or(0)) {
-                }
-            } else {
-                for (int k = 0; k < PW; ++k) __syncthreads();
-            }
-        }
+    // A warp without a unit has nothing to do -- unless the CTA's warps walk in step: then it goes through the code
+    // below with no problem in any slot, so that every warp of the CTA executes the SAME barrier instructions the
+    // same number of times (a block barrier in conditional code is defined only if the whole block takes it).
+    if (base >= n_active && !lockstep && !lockstep_rep) {
     } else {
     if (lane < PW) {
         const int64_t idx = base + lane;
@@ -952,7 +957,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
             double previous_cost = 0.0;
             for (int step = 0; step < c_pr.gd_max_iters; ++step) {
                 if (lockstep) {
-                    __syncthreads();
+                    block_barrier();
                 } else if (!__any_sync(kFull, going)) {
                     break;
                 }
@@ -1007,7 +1012,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
     const int G = (PW > 1 && !c_rb.any_unbounded && (c_pr.lockstep & 8) == 0) ? PW : 1;
     const int LG = 32 / G;
     for (int k0 = 0; k0 < PW; k0 += G) {
-        if (lockstep_rep && G == 1) __syncthreads();  // re-align the CTA's warps at every problem (instruction-cache sharing)
+        if (lockstep_rep && G == 1) block_barrier();  // re-align the CTA's warps at every problem (instruction-cache sharing)
         const bool in_group = lane / LG < G;  // (32 / G lanes per problem: E = 5 leaves lanes 30 and 31 out)
         const int kk = in_group ? k0 + lane / LG : k0;  // this lane's problem slot
         const int gl = lane % LG;
@@ -1066,7 +1071,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
             const bool actv = i < P;
             const bool any = __any_sync(kFull, actv);
             if (lockstep_rep && G > 1) {
-                if (!__syncthreads_or(any)) break;  // the CTA's warps walk their windows in step
+                if (!block_barrier_or(any)) break;  // the CTA's warps walk their windows in step
                 if (!any) continue;
             } else if (!any) {
                 break;
@@ -1138,6 +1143,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
             const double fl = __shfl_sync(kFull, f, from);
             const int a = __shfl_sync(kFull, ia, from), bb = __shfl_sync(kFull, ib, from);
             const bool commit = actv && gl <= l;
+            __syncwarp();  // every lane has read the group's pool and next-child entries
             if (gl == 0 && actv) {
                 if (gmask) {
                     int p2 = ps;
@@ -1369,7 +1375,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
             int steps = gd_steps;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(kFull, steps, o);
-            if (lane == 0) {
+            if (lane == 0 && n_problems > 0) {
                 atomicAdd(&sb.stats[0], (unsigned long long)n_problems);
                 atomicAdd(&sb.stats[1], (unsigned long long)steps);
             }
@@ -1395,7 +1401,7 @@ __global__ void __launch_bounds__(S::kWide ? 128 : 32 * kWarpsPerBlockBulk, S::k
     }
   }
     }  // this warp's unit
-    __syncthreads();  // s_claim is rewritten by the next claim
+    block_barrier();  // s_claim is rewritten by the next claim
   }
 }
 
